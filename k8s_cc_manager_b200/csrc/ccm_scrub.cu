@@ -1,0 +1,653 @@
+// ccm_scrub.cu — host side of the HBM scrub-and-verify stage: per-device engines
+// (primary context + stream + events + counter), the arena that holds "all the HBM
+// a context can map", launch-shape selection and the dispatch onto the sm_100a
+// kernels in scrub_kernels.cuh.
+//
+// No reference counterpart: SURVEY.md §0 / §8a row S (the reference stops at
+// verify-mode, reference main.py:521-529).  There is NO host fallback anywhere in
+// this file: without a usable CUDA device every entry point returns
+// CCM_ERR_NO_CUDA / CCM_ERR_CUDA.
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "ccm_internal.h"
+#include "scrub_kernels.cuh"
+
+namespace ccm {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launches() { return g_launches.load(); }
+
+#define CCM_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return e__ == cudaErrorMemoryAllocation ? CCM_ERR_NOMEM : CCM_ERR_CUDA;       \
+    }                                                                               \
+  } while (0)
+
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int cuda_device_count() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int cuda_describe(int ordinal, char* bdf, size_t bdf_cap, char* name, size_t name_cap,
+                  uint64_t* total_bytes) {
+  cudaDeviceProp prop;
+  CCM_CUDA(cudaGetDeviceProperties(&prop, ordinal));
+  char bus[64] = {0};
+  CCM_CUDA(cudaDeviceGetPCIBusId(bus, sizeof bus, ordinal));
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  snprintf(bdf, bdf_cap, "%s", bus);
+  snprintf(name, name_cap, "%s", prop.name);
+  if (total_bytes) *total_bytes = prop.totalGlobalMem;
+  return CCM_OK;
+}
+
+// --------------------------------------------------------------------- engine
+struct Segment { uint8_t* ptr; uint64_t bytes; };
+
+static constexpr int kMaxSteps = 64;
+
+struct ScrubEngine {
+  int ordinal = -1;
+  std::mutex mu;
+  bool ready = false;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;   // the engine's own non-blocking stream
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t step_ev[kMaxSteps][3];
+  int step_count = 0;
+  unsigned long long* d_counter = nullptr;
+  unsigned long long* h_counter = nullptr;  // pinned
+  std::vector<Segment> segs;
+  uint64_t arena_bytes = 0;
+  size_t total_bytes = 0;
+
+  int init() {
+    if (ready) return CCM_OK;
+    CCM_CUDA(cudaSetDevice(ordinal));
+    CCM_CUDA(cudaFree(0));  // force primary-context creation here, not inside a timed call
+    int v = 0;
+    CCM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ordinal));
+    sm_count = v;
+    CCM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ordinal));
+    smem_optin = (size_t)v;
+    CCM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CCM_CUDA(cudaEventCreate(&e));
+    for (auto& s : step_ev) for (auto& e : s) CCM_CUDA(cudaEventCreate(&e));
+    CCM_CUDA(cudaMalloc(&d_counter, 256));
+    CCM_CUDA(cudaMemset(d_counter, 0, 256));
+    CCM_CUDA(cudaHostAlloc(&h_counter, 64, cudaHostAllocDefault));
+    size_t fr = 0;
+    CCM_CUDA(cudaMemGetInfo(&fr, &total_bytes));
+    ready = true;
+    return CCM_OK;
+  }
+  cudaStream_t pick(void* s) const { return s ? (cudaStream_t)s : stream; }
+};
+
+static std::mutex g_engines_mu;
+static std::vector<std::unique_ptr<ScrubEngine>> g_engines;
+
+ScrubEngine* engine_for(int ordinal) {
+  if (ordinal < 0) { set_error("device has no CUDA ordinal"); return nullptr; }
+  ScrubEngine* e = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_engines_mu);
+    if ((size_t)ordinal >= g_engines.size()) {
+      int n = cuda_device_count();
+      if (ordinal >= n) { set_error("CUDA ordinal %d not present (%d devices)", ordinal, n); return nullptr; }
+      while (g_engines.size() < (size_t)n) {
+        g_engines.emplace_back(new ScrubEngine());
+        g_engines.back()->ordinal = (int)g_engines.size() - 1;
+      }
+    }
+    e = g_engines[ordinal].get();
+  }
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->init() != CCM_OK) return nullptr;
+  return e;
+}
+
+// ------------------------------------------------------------- launch shapes
+struct Shape { int ctas_per_sm, threads, unroll, policy, tile_bytes; };
+
+// Defaults; the numbers come from the sweeps recorded in profiles/ (DESIGN.md §5).
+static Shape scrub_shape(int variant, const ccm_launch_cfg* c) {
+  Shape s;
+  if (variant == CCM_SCRUB_TMA) s = Shape{1, 128, 0, kPolDefault, 32768};
+  else s = Shape{8, 256, 4, kPolDefault, 0};
+  if (c) {
+    if (c->ctas_per_sm > 0) s.ctas_per_sm = c->ctas_per_sm;
+    if (c->threads_per_cta > 0) s.threads = c->threads_per_cta;
+    if (c->unroll > 0) s.unroll = c->unroll;
+    if (c->cache_policy >= 1 && c->cache_policy <= 4) s.policy = c->cache_policy - 1;
+    if (c->tile_bytes > 0) s.tile_bytes = c->tile_bytes;
+  }
+  return s;
+}
+static Shape verify_shape(int variant, const ccm_launch_cfg* c) {
+  Shape s;
+  if (variant == CCM_VERIFY_TMA) s = Shape{2, 288, 0, kPolDefault, 16384};
+  else s = Shape{4, 512, 4, kPolStreaming, 0};
+  if (c) {
+    if (c->ctas_per_sm > 0) s.ctas_per_sm = c->ctas_per_sm;
+    if (c->threads_per_cta > 0) s.threads = c->threads_per_cta;
+    if (c->unroll > 0) s.unroll = c->unroll;
+    if (c->cache_policy >= 1 && c->cache_policy <= 4) s.policy = c->cache_policy - 1;
+    if (c->tile_bytes > 0) s.tile_bytes = c->tile_bytes;
+  }
+  return s;
+}
+
+static int resolve_scrub_variant(int v) { return v == CCM_SCRUB_AUTO ? CCM_SCRUB_ST256 : v; }
+static int resolve_verify_variant(int v) { return v == CCM_VERIFY_AUTO ? CCM_VERIFY_LD256 : v; }
+
+template <int VB, int UNROLL>
+static cudaError_t launch_scrub_st_pol(const RegionSplit& s, int grid, int threads, int pol, cudaStream_t st) {
+  switch (pol) {
+    case kPolEvictFirst: scrub_st_kernel<VB, UNROLL, kPolEvictFirst><<<grid, threads, 0, st>>>(s); break;
+    case kPolStreaming:  scrub_st_kernel<VB, UNROLL, kPolStreaming><<<grid, threads, 0, st>>>(s); break;
+    case kPolEvictLast:  scrub_st_kernel<VB, UNROLL, kPolEvictLast><<<grid, threads, 0, st>>>(s); break;
+    default:             scrub_st_kernel<VB, UNROLL, kPolDefault><<<grid, threads, 0, st>>>(s); break;
+  }
+  return cudaGetLastError();
+}
+template <int VB>
+static cudaError_t launch_scrub_st(const RegionSplit& s, int grid, const Shape& sh, cudaStream_t st) {
+  switch (sh.unroll) {
+    case 1: return launch_scrub_st_pol<VB, 1>(s, grid, sh.threads, sh.policy, st);
+    case 2: return launch_scrub_st_pol<VB, 2>(s, grid, sh.threads, sh.policy, st);
+    case 8: return launch_scrub_st_pol<VB, 8>(s, grid, sh.threads, sh.policy, st);
+    case 16: return launch_scrub_st_pol<VB, 16>(s, grid, sh.threads, sh.policy, st);
+    default: return launch_scrub_st_pol<VB, 4>(s, grid, sh.threads, sh.policy, st);
+  }
+}
+
+template <int VB, int UNROLL>
+static cudaError_t launch_verify_ld_pol(const RegionSplit& s, int grid, int threads, int pol,
+                                        unsigned long long* ctr, cudaStream_t st) {
+  switch (pol) {
+    case kPolEvictFirst: verify_ld_kernel<VB, UNROLL, kPolEvictFirst><<<grid, threads, 0, st>>>(s, ctr); break;
+    case kPolStreaming:  verify_ld_kernel<VB, UNROLL, kPolStreaming><<<grid, threads, 0, st>>>(s, ctr); break;
+    case kPolEvictLast:  verify_ld_kernel<VB, UNROLL, kPolEvictLast><<<grid, threads, 0, st>>>(s, ctr); break;
+    default:             verify_ld_kernel<VB, UNROLL, kPolDefault><<<grid, threads, 0, st>>>(s, ctr); break;
+  }
+  return cudaGetLastError();
+}
+template <int VB>
+static cudaError_t launch_verify_ld(const RegionSplit& s, int grid, const Shape& sh,
+                                    unsigned long long* ctr, cudaStream_t st) {
+  switch (sh.unroll) {
+    case 1: return launch_verify_ld_pol<VB, 1>(s, grid, sh.threads, sh.policy, ctr, st);
+    case 2: return launch_verify_ld_pol<VB, 2>(s, grid, sh.threads, sh.policy, ctr, st);
+    case 8: return launch_verify_ld_pol<VB, 8>(s, grid, sh.threads, sh.policy, ctr, st);
+    default: return launch_verify_ld_pol<VB, 4>(s, grid, sh.threads, sh.policy, ctr, st);
+  }
+}
+
+static int clamp_threads(int t) {
+  if (t < 32) t = 32;
+  if (t > 1024) t = 1024;
+  return (t / 32) * 32;
+}
+
+// Scrub one contiguous range on `st` (no sync).
+static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const ccm_launch_cfg* cfg,
+                       cudaStream_t st) {
+  if (n == 0) return CCM_OK;
+  variant = resolve_scrub_variant(variant);
+  Shape sh = scrub_shape(variant, cfg);
+  sh.threads = clamp_threads(sh.threads);
+  const int grid = e->sm_count * (sh.ctas_per_sm > 0 ? sh.ctas_per_sm : 1);
+  cudaError_t err = cudaSuccess;
+  switch (variant) {
+    case CCM_SCRUB_MEMSET:
+      err = cudaMemsetAsync(p, 0, n, st);
+      break;
+    case CCM_SCRUB_ST128: {
+      RegionSplit s = split_region(p, n, 16, 128);
+      err = launch_scrub_st<16>(s, grid, sh, st);
+      g_launches++;
+      break;
+    }
+    case CCM_SCRUB_ST256: {
+      RegionSplit s = split_region(p, n, 32, 128);
+      err = launch_scrub_st<32>(s, grid, sh, st);
+      g_launches++;
+      break;
+    }
+    case CCM_SCRUB_TMA: {
+      RegionSplit s = split_region(p, n, 16, 128);
+      uint32_t tile = (uint32_t)sh.tile_bytes & ~15u;
+      if (tile < 1024) tile = 1024;
+      if (tile > e->smem_optin - 1024) tile = (uint32_t)((e->smem_optin - 1024) & ~127ull);
+      const int threads = sh.threads > 256 ? 256 : sh.threads;
+      const uint32_t ops_per_group = sh.unroll > 0 ? (uint32_t)sh.unroll : 4;
+      const uint32_t inflight = 0;  // unbounded: drain once at exit
+#define CCM_TMA_LAUNCH(POL)                                                                       \
+      do {                                                                                        \
+        err = cudaFuncSetAttribute(scrub_tma_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile); \
+        if (err == cudaSuccess) {                                                                 \
+          scrub_tma_kernel<POL><<<grid, threads, tile, st>>>(s, tile, ops_per_group, inflight);   \
+          err = cudaGetLastError();                                                               \
+        }                                                                                         \
+      } while (0)
+      if (sh.policy == kPolEvictFirst) CCM_TMA_LAUNCH(kPolEvictFirst);
+      else if (sh.policy == kPolEvictLast) CCM_TMA_LAUNCH(kPolEvictLast);
+      else CCM_TMA_LAUNCH(kPolDefault);
+#undef CCM_TMA_LAUNCH
+      g_launches++;
+      break;
+    }
+    default:
+      set_error("unknown scrub variant %d", variant);
+      return CCM_ERR_INVALID;
+  }
+  if (err != cudaSuccess) {
+    set_error("scrub launch (variant %d) failed: %s", variant, cudaGetErrorString(err));
+    return CCM_ERR_CUDA;
+  }
+  return CCM_OK;
+}
+
+// Accumulate the non-zero byte count of one range into e->d_counter (no sync).
+static int verify_range(ScrubEngine* e, const void* p, uint64_t n, int variant, const ccm_launch_cfg* cfg,
+                        cudaStream_t st) {
+  if (n == 0) return CCM_OK;
+  variant = resolve_verify_variant(variant);
+  Shape sh = verify_shape(variant, cfg);
+  sh.threads = clamp_threads(sh.threads);
+  const int grid = e->sm_count * (sh.ctas_per_sm > 0 ? sh.ctas_per_sm : 1);
+  cudaError_t err = cudaSuccess;
+  switch (variant) {
+    case CCM_VERIFY_LD128: {
+      RegionSplit s = split_region(p, n, 16, 128);
+      err = launch_verify_ld<16>(s, grid, sh, e->d_counter, st);
+      break;
+    }
+    case CCM_VERIFY_LD256: {
+      RegionSplit s = split_region(p, n, 32, 128);
+      err = launch_verify_ld<32>(s, grid, sh, e->d_counter, st);
+      break;
+    }
+    case CCM_VERIFY_TMA: {
+      RegionSplit s = split_region(p, n, 16, 128);
+      constexpr int STAGES = 4;
+      uint32_t tile = (uint32_t)sh.tile_bytes & ~127u;
+      if (tile < 1024) tile = 1024;
+      const size_t maxsm = (e->smem_optin - 2048) / (size_t)sh.ctas_per_sm;
+      if ((size_t)tile * STAGES > maxsm) tile = (uint32_t)((maxsm / STAGES) & ~127ull);
+      int threads = sh.threads < 64 ? 64 : sh.threads;
+      err = cudaFuncSetAttribute(verify_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(tile * STAGES));
+      if (err == cudaSuccess) {
+        verify_tma_kernel<STAGES><<<grid, threads, tile * STAGES, st>>>(s, tile, e->d_counter);
+        err = cudaGetLastError();
+      }
+      break;
+    }
+    default:
+      set_error("unknown verify variant %d", variant);
+      return CCM_ERR_INVALID;
+  }
+  g_launches++;
+  if (err != cudaSuccess) {
+    set_error("verify launch (variant %d) failed: %s", variant, cudaGetErrorString(err));
+    return CCM_ERR_CUDA;
+  }
+  return CCM_OK;
+}
+
+// ----------------------------------------------------------------------- arena
+static constexpr uint64_t kMiB = 1ull << 20;
+
+static uint64_t env_u64(const char* name, uint64_t dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return strtoull(v, nullptr, 10);
+}
+
+int engine_arena_release(ScrubEngine* e, double* ms) {
+  std::lock_guard<std::mutex> g(e->mu);
+  const double t0 = now_ms();
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  int rc = CCM_OK;
+  for (auto& s : e->segs) {
+    cudaError_t err = cudaFree(s.ptr);
+    if (err != cudaSuccess) { set_error("cudaFree failed: %s", cudaGetErrorString(err)); rc = CCM_ERR_CUDA; }
+  }
+  e->segs.clear();
+  e->arena_bytes = 0;
+  if (ms) *ms = now_ms() - t0;
+  return rc;
+}
+
+int engine_arena_acquire(ScrubEngine* e, uint64_t bytes, ccm_arena_info* out) {
+  std::lock_guard<std::mutex> g(e->mu);
+  if (!e->segs.empty()) { set_error("arena already held on CUDA device %d", e->ordinal); return CCM_ERR_STATE; }
+  const double t0 = now_ms();
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  size_t fr = 0, tot = 0;
+  CCM_CUDA(cudaMemGetInfo(&fr, &tot));
+  e->total_bytes = tot;
+  const bool want_max = (bytes == 0);
+  // Leave a little HBM for the driver (launch-time local memory, event pools).
+  const uint64_t reserve = env_u64("CCM_ARENA_RESERVE_MB", 256) * kMiB;
+  uint64_t want = bytes;
+  if (want_max) want = fr > reserve ? ((fr - reserve) & ~(2 * kMiB - 1)) : 0;
+  if (want == 0) { set_error("no free HBM to scrub (free=%zu)", fr); return CCM_ERR_NOMEM; }
+
+  // First choice: ONE contiguous virtual range.  Fall back to a segment list
+  // (largest-first, halving) when HBM is fragmented.
+  uint8_t* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, want);
+  if (err == cudaSuccess) {
+    e->segs.push_back({p, want});
+    e->arena_bytes = want;
+  } else {
+    cudaGetLastError();
+    uint64_t got = 0, chunk = 16ull << 30;
+    while (got < want && chunk >= 64 * kMiB) {
+      uint64_t ask = want - got < chunk ? want - got : chunk;
+      if (!want_max && ask < chunk && ask < 64 * kMiB) { /* small exact tail */ }
+      err = cudaMalloc(&p, ask);
+      if (err == cudaSuccess) { e->segs.push_back({p, ask}); got += ask; }
+      else { cudaGetLastError(); chunk >>= 1; }
+    }
+    if (!want_max && got < want) {
+      for (auto& s : e->segs) cudaFree(s.ptr);
+      e->segs.clear();
+      set_error("could not obtain %llu bytes of HBM on CUDA device %d (free %zu)",
+                (unsigned long long)want, e->ordinal, fr);
+      return CCM_ERR_NOMEM;
+    }
+    if (got == 0) { set_error("could not obtain any HBM on CUDA device %d", e->ordinal); return CCM_ERR_NOMEM; }
+    e->arena_bytes = got;
+  }
+  if (out) {
+    out->bytes = e->arena_bytes;
+    out->device_total_bytes = tot;
+    out->device_free_before = fr;
+    out->segments = (int)e->segs.size();
+    out->reserved = 0;
+    out->ms_acquire = now_ms() - t0;
+  }
+  return CCM_OK;
+}
+
+static int need_arena(ScrubEngine* e) {
+  if (e->segs.empty()) { set_error("no arena held on CUDA device %d", e->ordinal); return CCM_ERR_STATE; }
+  return CCM_OK;
+}
+
+int engine_arena_scrub(ScrubEngine* e, int variant, const ccm_launch_cfg* cfg, void* stream, float* ms) {
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = need_arena(e); if (rc) return rc;
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  cudaStream_t st = e->pick(stream);
+  if (ms) CCM_CUDA(cudaEventRecord(e->ev[0], st));
+  for (auto& s : e->segs) { rc = scrub_range(e, s.ptr, s.bytes, variant, cfg, st); if (rc) return rc; }
+  if (ms) {
+    CCM_CUDA(cudaEventRecord(e->ev[1], st));
+    CCM_CUDA(cudaEventSynchronize(e->ev[1]));
+    CCM_CUDA(cudaEventElapsedTime(ms, e->ev[0], e->ev[1]));
+  }
+  return CCM_OK;
+}
+
+static int fetch_count_locked(ScrubEngine* e, cudaStream_t st, uint64_t* nonzero) {
+  CCM_CUDA(cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CCM_CUDA(cudaStreamSynchronize(st));
+  if (nonzero) *nonzero = (uint64_t)*e->h_counter;
+  return CCM_OK;
+}
+
+int engine_arena_verify(ScrubEngine* e, int variant, const ccm_launch_cfg* cfg, void* stream,
+                        uint64_t* nonzero, float* ms) {
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = need_arena(e); if (rc) return rc;
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  cudaStream_t st = e->pick(stream);
+  CCM_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st));
+  CCM_CUDA(cudaEventRecord(e->ev[0], st));
+  for (auto& s : e->segs) { rc = verify_range(e, s.ptr, s.bytes, variant, cfg, st); if (rc) return rc; }
+  CCM_CUDA(cudaEventRecord(e->ev[1], st));
+  rc = fetch_count_locked(e, st, nonzero); if (rc) return rc;
+  if (ms) CCM_CUDA(cudaEventElapsedTime(ms, e->ev[0], e->ev[1]));
+  return CCM_OK;
+}
+
+int engine_arena_scrub_verify_async(ScrubEngine* e, int sv, int vv, const ccm_launch_cfg* scfg,
+                                    const ccm_launch_cfg* vcfg, void* stream) {
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = need_arena(e); if (rc) return rc;
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  cudaStream_t st = e->pick(stream);
+  cudaEvent_t* evs = e->step_count < kMaxSteps ? e->step_ev[e->step_count] : nullptr;
+  if (evs) CCM_CUDA(cudaEventRecord(evs[0], st));
+  for (auto& s : e->segs) { rc = scrub_range(e, s.ptr, s.bytes, sv, scfg, st); if (rc) return rc; }
+  CCM_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st));
+  if (evs) CCM_CUDA(cudaEventRecord(evs[1], st));
+  for (auto& s : e->segs) { rc = verify_range(e, s.ptr, s.bytes, vv, vcfg, st); if (rc) return rc; }
+  if (evs) { CCM_CUDA(cudaEventRecord(evs[2], st)); e->step_count++; }
+  return CCM_OK;
+}
+
+int engine_arena_step_times(ScrubEngine* e, int cap, float* scrub_ms, float* verify_ms, int* n) {
+  std::lock_guard<std::mutex> g(e->mu);
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  int k = e->step_count < cap ? e->step_count : cap;
+  for (int i = 0; i < k; ++i) {
+    CCM_CUDA(cudaEventSynchronize(e->step_ev[i][2]));
+    if (scrub_ms) CCM_CUDA(cudaEventElapsedTime(&scrub_ms[i], e->step_ev[i][0], e->step_ev[i][1]));
+    if (verify_ms) CCM_CUDA(cudaEventElapsedTime(&verify_ms[i], e->step_ev[i][1], e->step_ev[i][2]));
+  }
+  if (n) *n = k;
+  e->step_count = 0;
+  return CCM_OK;
+}
+
+int engine_arena_fetch_count(ScrubEngine* e, void* stream, uint64_t* nonzero) {
+  std::lock_guard<std::mutex> g(e->mu);
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  return fetch_count_locked(e, e->pick(stream), nonzero);
+}
+
+__global__ void fill_byte_kernel(uint4* p, uint64_t nvec, uint32_t word) {
+  const uint4 v = make_uint4(word, word, word, word);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+int engine_arena_fill(ScrubEngine* e, int byte_value, void* stream) {
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = need_arena(e); if (rc) return rc;
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  cudaStream_t st = e->pick(stream);
+  const uint32_t b = (uint32_t)(byte_value & 0xff);
+  const uint32_t word = b | (b << 8) | (b << 16) | (b << 24);
+  for (auto& s : e->segs) {
+    const uint64_t nvec = s.bytes / 16;
+    if (nvec) { fill_byte_kernel<<<e->sm_count * 8, 256, 0, st>>>((uint4*)s.ptr, nvec, word); g_launches++; }
+    const uint64_t rem = s.bytes - nvec * 16;
+    if (rem) CCM_CUDA(cudaMemsetAsync(s.ptr + nvec * 16, (int)b, rem, st));
+    CCM_CUDA(cudaGetLastError());
+  }
+  CCM_CUDA(cudaStreamSynchronize(st));
+  return CCM_OK;
+}
+
+int engine_arena_fill_random(ScrubEngine* e, uint64_t seed, void* stream) {
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = need_arena(e); if (rc) return rc;
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  cudaStream_t st = e->pick(stream);
+  uint64_t word0 = 0;
+  for (auto& s : e->segs) {
+    const uint64_t nwords = s.bytes / 8;
+    if (nwords) { fill_pattern_kernel<<<e->sm_count * 8, 256, 0, st>>>((uint64_t*)s.ptr, nwords, word0, seed); g_launches++; }
+    const uint64_t rem = s.bytes - nwords * 8;  // trailing bytes of the pattern are zero
+    if (rem) CCM_CUDA(cudaMemsetAsync(s.ptr + nwords * 8, 0, rem, st));
+    CCM_CUDA(cudaGetLastError());
+    word0 += nwords;
+  }
+  CCM_CUDA(cudaStreamSynchronize(st));
+  return CCM_OK;
+}
+
+int engine_arena_rw(ScrubEngine* e, uint64_t offset, void* host, uint64_t bytes, bool write) {
+  std::lock_guard<std::mutex> g(e->mu);
+  int rc = need_arena(e); if (rc) return rc;
+  if (offset + bytes > e->arena_bytes || offset + bytes < offset) {
+    set_error("arena access [%llu,+%llu) outside %llu bytes", (unsigned long long)offset,
+              (unsigned long long)bytes, (unsigned long long)e->arena_bytes);
+    return CCM_ERR_INVALID;
+  }
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  uint8_t* h = (uint8_t*)host;
+  uint64_t seg_start = 0;
+  for (auto& s : e->segs) {
+    const uint64_t seg_end = seg_start + s.bytes;
+    if (bytes && offset < seg_end && offset + bytes > seg_start) {
+      const uint64_t a = offset > seg_start ? offset : seg_start;
+      const uint64_t b = offset + bytes < seg_end ? offset + bytes : seg_end;
+      if (write) CCM_CUDA(cudaMemcpy(s.ptr + (a - seg_start), h + (a - offset), b - a, cudaMemcpyHostToDevice));
+      else CCM_CUDA(cudaMemcpy(h + (a - offset), s.ptr + (a - seg_start), b - a, cudaMemcpyDeviceToHost));
+    }
+    seg_start = seg_end;
+  }
+  return CCM_OK;
+}
+
+// --------------------------------------------------------------- product call
+int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* out) {
+  const double t0 = now_ms();
+  ccm_scrub_result r;
+  memset(&r, 0, sizeof r);
+  r.bytes_requested = bytes;
+  r.sm_count = e->sm_count;
+  r.scrub_variant = resolve_scrub_variant(CCM_SCRUB_AUTO);
+  r.verify_variant = resolve_verify_variant(CCM_VERIFY_AUTO);
+  ccm_arena_info ai;
+  int rc = engine_arena_acquire(e, bytes, &ai);
+  if (rc == CCM_OK) {
+    r.ms_acquire = ai.ms_acquire;
+    r.bytes_scrubbed = ai.bytes;
+    r.device_total_bytes = ai.device_total_bytes;
+    r.segments = ai.segments;
+    float ms_s = 0, ms_v = 0;
+    uint64_t nz = 0;
+    rc = engine_arena_scrub(e, CCM_SCRUB_AUTO, nullptr, nullptr, &ms_s);
+    if (rc == CCM_OK) rc = engine_arena_verify(e, CCM_VERIFY_AUTO, nullptr, nullptr, &nz, &ms_v);
+    r.ms_scrub = ms_s;
+    r.ms_verify = ms_v;
+    r.nonzero_bytes = nz;
+    int rc2 = engine_arena_release(e, &r.ms_release);
+    if (rc == CCM_OK) rc = rc2;
+    if (rc == CCM_OK && nz != 0) {
+      set_error("scrub verify found %llu non-zero bytes on CUDA device %d", (unsigned long long)nz, e->ordinal);
+      rc = CCM_ERR_DIRTY;
+    }
+  }
+  r.ms_total = now_ms() - t0;
+  r.status = rc;
+  if (out) *out = r;
+  return rc;
+}
+
+// ----------------------------------------------------------------- raw regions
+int engine_region_scrub(ScrubEngine* e, void* dptr, uint64_t bytes, int variant, const ccm_launch_cfg* cfg,
+                        void* stream, float* ms) {
+  std::lock_guard<std::mutex> g(e->mu);
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  cudaStream_t st = e->pick(stream);
+  if (ms) CCM_CUDA(cudaEventRecord(e->ev[0], st));
+  int rc = scrub_range(e, dptr, bytes, variant, cfg, st);
+  if (rc) return rc;
+  if (ms) {
+    CCM_CUDA(cudaEventRecord(e->ev[1], st));
+    CCM_CUDA(cudaEventSynchronize(e->ev[1]));
+    CCM_CUDA(cudaEventElapsedTime(ms, e->ev[0], e->ev[1]));
+  }
+  return CCM_OK;
+}
+
+int engine_region_verify(ScrubEngine* e, const void* dptr, uint64_t bytes, int variant,
+                         const ccm_launch_cfg* cfg, void* stream, uint64_t* nonzero, float* ms) {
+  std::lock_guard<std::mutex> g(e->mu);
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  cudaStream_t st = e->pick(stream);
+  CCM_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st));
+  CCM_CUDA(cudaEventRecord(e->ev[0], st));
+  int rc = verify_range(e, dptr, bytes, variant, cfg, st);
+  if (rc) return rc;
+  CCM_CUDA(cudaEventRecord(e->ev[1], st));
+  rc = fetch_count_locked(e, st, nonzero);
+  if (rc) return rc;
+  if (ms) CCM_CUDA(cudaEventElapsedTime(ms, e->ev[0], e->ev[1]));
+  return CCM_OK;
+}
+
+int engine_host_roundtrip(ScrubEngine* e, void* host_buf, uint64_t bytes, uint64_t dev_offset,
+                          int sv, int vv, uint64_t* pre, uint64_t* post) {
+  std::lock_guard<std::mutex> g(e->mu);
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  cudaStream_t st = e->stream;
+  uint8_t* d = nullptr;
+  // dev_offset shifts the region off the allocation's natural alignment so ragged
+  // heads are exercised; the guard bytes around it must stay untouched.
+  const uint64_t guard = 256;
+  const uint64_t alloc = guard + dev_offset + bytes + guard;
+  CCM_CUDA(cudaMalloc(&d, alloc));
+  int rc = CCM_OK;
+  auto fail = [&](cudaError_t err, const char* what) {
+    set_error("%s failed: %s", what, cudaGetErrorString(err));
+    rc = CCM_ERR_CUDA;
+  };
+  cudaError_t err;
+  uint8_t* region = d + guard + dev_offset;
+  std::vector<uint8_t> g0(guard + dev_offset, 0xEE), g1(guard, 0xEE), chk;
+  do {
+    if ((err = cudaMemsetAsync(d, 0xEE, alloc, st)) != cudaSuccess) { fail(err, "memset guard"); break; }
+    if (bytes && (err = cudaMemcpyAsync(region, host_buf, bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) { fail(err, "H2D"); break; }
+    if (pre) {
+      if ((err = cudaMemsetAsync(e->d_counter, 0, 8, st)) != cudaSuccess) { fail(err, "counter"); break; }
+      if ((rc = verify_range(e, region, bytes, vv, nullptr, st))) break;
+      if ((rc = fetch_count_locked(e, st, pre))) break;
+    }
+    if ((rc = scrub_range(e, region, bytes, sv, nullptr, st))) break;
+    if ((err = cudaMemsetAsync(e->d_counter, 0, 8, st)) != cudaSuccess) { fail(err, "counter"); break; }
+    if ((rc = verify_range(e, region, bytes, vv, nullptr, st))) break;
+    if ((rc = fetch_count_locked(e, st, post))) break;
+    if (bytes && (err = cudaMemcpy(host_buf, region, bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) { fail(err, "D2H"); break; }
+    // guards: the scrub must not have written outside [region, region+bytes)
+    chk.resize(g0.size());
+    if ((err = cudaMemcpy(chk.data(), d, chk.size(), cudaMemcpyDeviceToHost)) != cudaSuccess) { fail(err, "D2H guard"); break; }
+    if (memcmp(chk.data(), g0.data(), g0.size()) != 0) { set_error("scrub wrote below the region"); rc = CCM_ERR_DIRTY; break; }
+    chk.resize(g1.size());
+    if ((err = cudaMemcpy(chk.data(), region + bytes, chk.size(), cudaMemcpyDeviceToHost)) != cudaSuccess) { fail(err, "D2H guard"); break; }
+    if (memcmp(chk.data(), g1.data(), g1.size()) != 0) { set_error("scrub wrote past the region"); rc = CCM_ERR_DIRTY; break; }
+  } while (0);
+  cudaFree(d);
+  return rc;
+}
+
+}  // namespace ccm

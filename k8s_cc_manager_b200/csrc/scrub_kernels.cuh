@@ -1,0 +1,439 @@
+// scrub_kernels.cuh — sm_100a kernels of the HBM scrub-and-verify stage.
+//
+// the reference has NO scrub (reference main.py:502-529 goes
+// stage -> reset -> wait -> verify-mode only); these kernels are the new stage
+// inserted after main.py:529.  Contract: after scrub every byte of the region is
+// 0x00; verify returns the EXACT number of bytes != 0 (u64).
+//
+// Bound: HBM bandwidth.  Integer / byte work only — no FP, no tensor cores (there
+// is no contraction).  Algorithmic bytes: scrub = R written, verify = R read.
+//
+// Region decomposition (any pointer, any length):
+//   [ head bytes | body: whole VB-byte vectors, VB-aligned | tail bytes ]
+// head/tail are < 128+VB bytes and are handled with byte accesses by CTA 0; the
+// body is tiled  tile = threads * UNROLL vectors  and grid-strided by persistent
+// CTAs (grid = ctas_per_sm * #SMs), so at any instant the whole chip writes one
+// moving window of grid*tile bytes (a few tens of MB: inside TLB reach, and every
+// warp instruction covers whole 128-byte lines -> only full-sector writes).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ccm {
+
+enum CachePolicy : int { kPolDefault = 0, kPolEvictFirst = 1, kPolStreaming = 2, kPolEvictLast = 3 };
+
+// ---------------------------------------------------------------- PTX wrappers
+// 128-bit stores/loads take an L2 eviction priority only through a createpolicy
+// cache hint (the bare .L2::evict_* qualifier is accepted on 256-bit forms only).
+template <int POL>
+__device__ __forceinline__ uint64_t make_l2_policy() {
+  uint64_t pol = 0;
+  if constexpr (POL == kPolEvictFirst)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  if constexpr (POL == kPolEvictLast)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+template <int POL>
+__device__ __forceinline__ void st_zero16(void* p, uint64_t l2pol) {
+  if constexpr (POL == kPolEvictFirst || POL == kPolEvictLast)
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%1,%1,%1}, %2;" ::"l"(p), "r"(0), "l"(l2pol) : "memory");
+  else if constexpr (POL == kPolStreaming)
+    asm volatile("st.global.cs.v4.b32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(0) : "memory");
+  else
+    asm volatile("st.global.v4.b32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(0) : "memory");
+}
+
+// 256-bit store: PTX 8.8, sm_100+ only (SASS: STG.E.256).
+template <int POL>
+__device__ __forceinline__ void st_zero32(void* p) {
+  if constexpr (POL == kPolEvictFirst)
+    asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(0) : "memory");
+  else if constexpr (POL == kPolStreaming)
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(0) : "memory");
+  else if constexpr (POL == kPolEvictLast)
+    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(0) : "memory");
+  else
+    asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(p), "r"(0) : "memory");
+}
+
+template <int VB, int POL>
+__device__ __forceinline__ void st_zero(void* p, uint64_t l2pol) {
+  if constexpr (VB == 32) st_zero32<POL>(p); else st_zero16<POL>(p, l2pol);
+}
+
+struct Vec16 { uint32_t w[4]; };
+struct Vec32 { uint32_t w[8]; };
+
+template <int POL>
+__device__ __forceinline__ Vec16 ld16(const void* p, uint64_t l2pol) {
+  Vec16 v;
+  if constexpr (POL == kPolEvictFirst || POL == kPolEvictLast)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p), "l"(l2pol));
+  else if constexpr (POL == kPolStreaming)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p));
+  else
+    asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p));
+  return v;
+}
+
+template <int POL>
+__device__ __forceinline__ Vec32 ld32(const void* p) {
+  Vec32 v;
+  if constexpr (POL == kPolEvictFirst)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]),
+                   "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7]) : "l"(p));
+  else if constexpr (POL == kPolStreaming)
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]),
+                   "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7]) : "l"(p));
+  else if constexpr (POL == kPolEvictLast)
+    asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]),
+                   "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7]) : "l"(p));
+  else
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]),
+                   "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7]) : "l"(p));
+  return v;
+}
+
+// Exact number of non-zero BYTES in a 32-bit word, branch-free:
+// bit 7 of each byte of m is set iff that byte != 0.
+__device__ __forceinline__ uint32_t nonzero_bytes_in_word(uint32_t w) {
+  uint32_t m = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+  return __popc(m);
+}
+
+// ------------------------------------------------------------------- layout
+struct RegionSplit {
+  uint8_t* base;       // region start
+  uint64_t head;       // bytes before the aligned body
+  uint64_t body_vecs;  // number of VB-byte vectors in the body
+  uint64_t tail;       // bytes after the body
+};
+
+__host__ __device__ inline RegionSplit split_region(const void* p, uint64_t n, int vb, int align) {
+  RegionSplit s;
+  s.base = (uint8_t*)p;
+  uint64_t mis = (uint64_t)(uintptr_t)p & (uint64_t)(align - 1);
+  uint64_t head = mis ? (uint64_t)align - mis : 0;
+  if (head > n) head = n;
+  s.head = head;
+  s.body_vecs = (n - head) / (uint64_t)vb;
+  s.tail = (n - head) - s.body_vecs * (uint64_t)vb;
+  return s;
+}
+
+// ------------------------------------------------------------- scrub (stores)
+template <int VB, int UNROLL, int POL>
+__global__ void __launch_bounds__(1024)
+scrub_st_kernel(RegionSplit s) {
+  uint8_t* body = s.base + s.head;
+  const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
+  const uint64_t ntiles = s.body_vecs / tile_vecs;
+  const uint64_t stride_bytes = (uint64_t)blockDim.x * VB;
+  const uint64_t l2pol = make_l2_policy<POL>();
+
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint8_t* p = body + (tile * tile_vecs + threadIdx.x) * VB;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) st_zero<VB, POL>(p + u * stride_bytes, l2pol);
+  }
+  // remainder vectors (< one tile), spread over the grid
+  for (uint64_t i = ntiles * tile_vecs + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+       i < s.body_vecs; i += (uint64_t)gridDim.x * blockDim.x)
+    st_zero<VB, POL>(body + i * VB, l2pol);
+  // ragged head / tail bytes
+  if (blockIdx.x == 0) {
+    for (uint64_t i = threadIdx.x; i < s.head; i += blockDim.x) s.base[i] = 0;
+    uint8_t* t = body + s.body_vecs * VB;
+    for (uint64_t i = threadIdx.x; i < s.tail; i += blockDim.x) t[i] = 0;
+  }
+}
+
+// ------------------------------------------------------ scrub (TMA bulk store)
+// One zeroed shared-memory tile per CTA is the source of EVERY bulk store: it
+// never changes, so there is no WAR hazard and no per-op wait — the issuing lane
+// streams cp.async.bulk.global.shared::cta ops (SASS: UBLKCP.G.S) grid-strided
+// over the body and drains them once at exit.
+template <int POL>
+__global__ void __launch_bounds__(256)
+scrub_tma_kernel(RegionSplit s /* VB = 16 */, uint32_t tile_bytes, uint32_t ops_per_group,
+                 uint32_t max_groups_in_flight) {
+  extern __shared__ __align__(128) uint8_t zero_tile[];
+  for (uint32_t i = threadIdx.x; i < tile_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(zero_tile)[i] = make_uint4(0, 0, 0, 0);
+  // make the generic-proxy smem writes visible to the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  uint8_t* body = s.base + s.head;
+  const uint64_t body_bytes = s.body_vecs * 16;
+  const uint64_t ntiles = body_bytes / tile_bytes;
+  const uint32_t last_bytes = (uint32_t)(body_bytes - ntiles * (uint64_t)tile_bytes);  // multiple of 16
+
+  // each WARP's lane 0 issues; warps interleave tiles so issue cost is spread.
+  const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(zero_tile);
+    uint64_t policy = 0;
+    if constexpr (POL == kPolEvictFirst)
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if constexpr (POL == kPolEvictLast)
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    uint32_t in_group = 0;
+    const uint64_t first = (uint64_t)blockIdx.x * nwarps + warp;
+    const uint64_t step = (uint64_t)gridDim.x * nwarps;
+    for (uint64_t tile = first; tile < ntiles; tile += step) {
+      uint8_t* dst = body + tile * (uint64_t)tile_bytes;
+      if constexpr (POL == kPolEvictFirst || POL == kPolEvictLast)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     ::"l"(dst), "r"(src), "r"(tile_bytes), "l"(policy) : "memory");
+      else
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(dst), "r"(src), "r"(tile_bytes) : "memory");
+      if (++in_group == ops_per_group) {
+        in_group = 0;
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // bound the number of committed-but-unfinished groups
+        switch (max_groups_in_flight) {
+          case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+          case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+          case 4: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+          case 8: asm volatile("cp.async.bulk.wait_group 8;" ::: "memory"); break;
+          default: break;  // unbounded: drain only at exit
+        }
+      }
+    }
+    if (last_bytes && blockIdx.x == 0 && warp == 0) {
+      uint8_t* dst = body + ntiles * (uint64_t)tile_bytes;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(dst), "r"(src), "r"(last_bytes) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if (blockIdx.x == 0) {
+    for (uint64_t i = threadIdx.x; i < s.head; i += blockDim.x) s.base[i] = 0;
+    uint8_t* t = body + body_bytes;
+    for (uint64_t i = threadIdx.x; i < s.tail; i += blockDim.x) t[i] = 0;
+  }
+}
+
+// ----------------------------------------------------------------- reductions
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One atomicAdd(u64) per CTA into the single device counter.
+__device__ __forceinline__ void block_accumulate(uint64_t cnt, unsigned long long* counter) {
+  __shared__ uint64_t warp_part[32];
+  cnt = warp_sum_u64(cnt);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) warp_part[warp] = cnt;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t v = lane < ((blockDim.x + 31) >> 5) ? warp_part[lane] : 0;
+    v = warp_sum_u64(v);
+    if (lane == 0 && v != 0) atomicAdd(counter, (unsigned long long)v);
+  }
+}
+
+// --------------------------------------------------------------- verify (loads)
+// All UNROLL loads are issued before any use (UNROLL*VB bytes in flight per
+// thread).  The expected answer is "all zero", so the hot loop only ORs the words
+// together; the exact per-byte count runs on the (rare) batches whose OR != 0.
+template <int VB, int UNROLL, int POL>
+__global__ void __launch_bounds__(1024)
+verify_ld_kernel(RegionSplit s, unsigned long long* counter) {
+  const uint8_t* body = s.base + s.head;
+  const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
+  const uint64_t ntiles = s.body_vecs / tile_vecs;
+  const uint64_t stride_bytes = (uint64_t)blockDim.x * VB;
+  constexpr int W = VB / 4;
+  uint64_t cnt = 0;
+  const uint64_t l2pol = make_l2_policy<POL>();
+  (void)l2pol;
+
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint8_t* p = body + (tile * tile_vecs + threadIdx.x) * VB;
+    uint32_t w[UNROLL][W];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if constexpr (VB == 32) {
+        Vec32 v = ld32<POL>(p + u * stride_bytes);
+#pragma unroll
+        for (int k = 0; k < W; ++k) w[u][k] = v.w[k];
+      } else {
+        Vec16 v = ld16<POL>(p + u * stride_bytes, l2pol);
+#pragma unroll
+        for (int k = 0; k < W; ++k) w[u][k] = v.w[k];
+      }
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int k = 0; k < W; ++k) any |= w[u][k];
+    if (any != 0) {
+      uint32_t c = 0;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int k = 0; k < W; ++k) c += nonzero_bytes_in_word(w[u][k]);
+      cnt += c;
+    }
+  }
+  for (uint64_t i = ntiles * tile_vecs + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+       i < s.body_vecs; i += (uint64_t)gridDim.x * blockDim.x) {
+    if constexpr (VB == 32) {
+      Vec32 v = ld32<POL>(body + i * VB);
+#pragma unroll
+      for (int k = 0; k < W; ++k) cnt += nonzero_bytes_in_word(v.w[k]);
+    } else {
+      Vec16 v = ld16<POL>(body + i * VB, l2pol);
+#pragma unroll
+      for (int k = 0; k < W; ++k) cnt += nonzero_bytes_in_word(v.w[k]);
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (uint64_t i = threadIdx.x; i < s.head; i += blockDim.x) cnt += (s.base[i] != 0);
+    const uint8_t* t = body + s.body_vecs * VB;
+    for (uint64_t i = threadIdx.x; i < s.tail; i += blockDim.x) cnt += (t[i] != 0);
+  }
+  block_accumulate(cnt, counter);
+}
+
+// ------------------------------------------------- verify (TMA bulk-load ring)
+// Producer lane streams cp.async.bulk.shared::cluster.global tiles into a
+// STAGES-deep smem ring (mbarrier complete_tx); all warps consume a stage with
+// 128-bit LDS, OR-reduce, and release it through an "empty" mbarrier.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra W_%=;\n\t}"
+      ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(1024)
+verify_tma_kernel(RegionSplit s /* VB = 16 */, uint32_t tile_bytes, unsigned long long* counter) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t nconsumer_warps = (blockDim.x >> 5) - 1;  // warp 0 is the producer
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], nconsumer_warps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint8_t* body = s.base + s.head;
+  const uint64_t body_bytes = s.body_vecs * 16;
+  const uint64_t ntiles = (body_bytes + tile_bytes - 1) / tile_bytes;  // last may be partial
+  // tiles owned by this CTA: blockIdx.x, +gridDim.x, ...
+  const uint64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  uint64_t cnt = 0;
+
+  auto tile_len = [&](uint64_t t) -> uint32_t {
+    uint64_t rem = body_bytes - t * (uint64_t)tile_bytes;
+    return rem < tile_bytes ? (uint32_t)rem : tile_bytes;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (uint64_t k = 0; k < my_tiles; ++k) {
+        const uint32_t stg = (uint32_t)(k % STAGES);
+        const uint64_t use = k / STAGES;
+        if (use > 0) mbar_wait(&empty_bar[stg], (uint32_t)((use - 1) & 1));
+        const uint64_t t = blockIdx.x + k * gridDim.x;
+        const uint32_t len = tile_len(t);
+        mbar_expect_tx(&full_bar[stg], len);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(ring + (size_t)stg * tile_bytes)),
+              "l"(body + t * (uint64_t)tile_bytes), "r"(len),
+              "r"((uint32_t)__cvta_generic_to_shared(&full_bar[stg])) : "memory");
+      }
+    }
+  } else {
+    const uint32_t ctid = threadIdx.x - 32, cthreads = blockDim.x - 32;
+    for (uint64_t k = 0; k < my_tiles; ++k) {
+      const uint32_t stg = (uint32_t)(k % STAGES);
+      mbar_wait(&full_bar[stg], (uint32_t)((k / STAGES) & 1));
+      const uint32_t len = tile_len(blockIdx.x + k * gridDim.x);
+      const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)stg * tile_bytes);
+      uint32_t c = 0;
+      for (uint32_t i = ctid; i < len / 16; i += cthreads) {
+        uint4 v = src[i];
+        if (v.x | v.y | v.z | v.w)
+          c += nonzero_bytes_in_word(v.x) + nonzero_bytes_in_word(v.y) +
+               nonzero_bytes_in_word(v.z) + nonzero_bytes_in_word(v.w);
+      }
+      cnt += c;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stg]);
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (uint64_t i = threadIdx.x; i < s.head; i += blockDim.x) cnt += (s.base[i] != 0);
+    const uint8_t* t = body + body_bytes;
+    for (uint64_t i = threadIdx.x; i < s.tail; i += blockDim.x) cnt += (t[i] != 0);
+  }
+  block_accumulate(cnt, counter);
+}
+
+// ------------------------------------------------------------ test scaffolding
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// Deterministic sparse pattern: 8-byte word j (arena-global index) is
+//   r = splitmix64(seed + j);  word = (r & 7) == 0 ? r & mask(r) : 0
+// where mask keeps a pseudo-random subset of the bytes.  The C oracle
+// (oracle/scrub_oracle.c: ccm_oracle_fill_random) restates the same formula.
+__host__ __device__ inline uint64_t pattern_word(uint64_t seed, uint64_t j) {
+  uint64_t x = seed + j;
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  x = x ^ (x >> 31);
+  if ((x & 7) != 0) return 0;
+  uint64_t keep = 0;
+  for (int b = 0; b < 8; ++b)
+    if ((x >> (8 + b)) & 1) keep |= 0xFFull << (8 * b);
+  return (x >> 3 | 0x0101010101010101ull) & keep;  // kept bytes are guaranteed non-zero
+}
+
+__global__ void fill_pattern_kernel(uint64_t* words, uint64_t nwords, uint64_t word_index0, uint64_t seed) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    words[i] = pattern_word(seed, word_index0 + i);
+}
+
+}  // namespace ccm
