@@ -155,11 +155,13 @@ typedef enum ccm_verify_variant {
 typedef struct ccm_launch_cfg {
   int32_t ctas_per_sm;
   int32_t threads_per_cta;
-  int32_t tile_bytes;   /* TMA variants: bytes per bulk op (multiple of 16)     */
+  int32_t tile_bytes;   /* TMA variants: bytes per bulk op (multiple of 16);
+                           ST/LD variants with a dynamic schedule: bytes per grab */
   int32_t unroll;       /* ST/LD variants: vectors in flight per thread (2,4,8) */
   int32_t cache_policy; /* 0 library default, 1 plain, 2 L2::evict_first,
                            3 streaming (.cs / L1::no_allocate), 4 L2::evict_last */
-  int32_t reserved;
+  int32_t schedule;     /* 0 library default, 1 static grid-stride, 2 dynamic
+                           (persistent CTAs grab chunks off an atomic counter)  */
 } ccm_launch_cfg;
 
 typedef struct ccm_scrub_result {

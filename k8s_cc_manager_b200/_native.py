@@ -68,7 +68,7 @@ class LaunchCfg(C.Structure):
         ("tile_bytes", C.c_int32),
         ("unroll", C.c_int32),
         ("cache_policy", C.c_int32),
-        ("reserved", C.c_int32),
+        ("schedule", C.c_int32),
     ]
 
 
@@ -194,6 +194,7 @@ def last_error() -> str:
 
 
 def launch_cfg(ctas_per_sm: int = 0, threads: int = 0, tile_bytes: int = 0, unroll: int = 0,
-               cache_policy: int = 0) -> LaunchCfg:
-    """cache_policy: 0 library default, 1 plain, 2 evict_first, 3 streaming, 4 evict_last."""
-    return LaunchCfg(ctas_per_sm, threads, tile_bytes, unroll, cache_policy, 0)
+               cache_policy: int = 0, schedule: int = 0) -> LaunchCfg:
+    """cache_policy: 0 library default, 1 plain, 2 evict_first, 3 streaming, 4 evict_last.
+    schedule: 0 library default, 1 static grid-stride, 2 dynamic (atomic chunk grabs)."""
+    return LaunchCfg(ctas_per_sm, threads, tile_bytes, unroll, cache_policy, schedule)

@@ -126,32 +126,34 @@ ScrubEngine* engine_for(int ordinal) {
 }
 
 // ------------------------------------------------------------- launch shapes
-struct Shape { int ctas_per_sm, threads, unroll, policy, tile_bytes; };
+struct Shape { int ctas_per_sm, threads, unroll, policy, tile_bytes, schedule; };  // schedule: 1 static, 2 dynamic
 
 // Defaults; the numbers come from the sweeps recorded in profiles/ (DESIGN.md §5).
 static Shape scrub_shape(int variant, const ccm_launch_cfg* c) {
   Shape s;
-  if (variant == CCM_SCRUB_TMA) s = Shape{1, 128, 0, kPolDefault, 32768};
-  else s = Shape{8, 256, 4, kPolDefault, 0};
+  if (variant == CCM_SCRUB_TMA) s = Shape{1, 128, 4, kPolDefault, 32768, 1};
+  else s = Shape{8, 256, 4, kPolDefault, 0, 1};
   if (c) {
     if (c->ctas_per_sm > 0) s.ctas_per_sm = c->ctas_per_sm;
     if (c->threads_per_cta > 0) s.threads = c->threads_per_cta;
     if (c->unroll > 0) s.unroll = c->unroll;
     if (c->cache_policy >= 1 && c->cache_policy <= 4) s.policy = c->cache_policy - 1;
     if (c->tile_bytes > 0) s.tile_bytes = c->tile_bytes;
+    if (c->schedule == 1 || c->schedule == 2) s.schedule = c->schedule;
   }
   return s;
 }
 static Shape verify_shape(int variant, const ccm_launch_cfg* c) {
   Shape s;
-  if (variant == CCM_VERIFY_TMA) s = Shape{2, 288, 0, kPolDefault, 16384};
-  else s = Shape{4, 512, 4, kPolStreaming, 0};
+  if (variant == CCM_VERIFY_TMA) s = Shape{2, 288, 0, kPolDefault, 16384, 1};
+  else s = Shape{4, 512, 4, kPolStreaming, 0, 1};
   if (c) {
     if (c->ctas_per_sm > 0) s.ctas_per_sm = c->ctas_per_sm;
     if (c->threads_per_cta > 0) s.threads = c->threads_per_cta;
     if (c->unroll > 0) s.unroll = c->unroll;
     if (c->cache_policy >= 1 && c->cache_policy <= 4) s.policy = c->cache_policy - 1;
     if (c->tile_bytes > 0) s.tile_bytes = c->tile_bytes;
+    if (c->schedule == 1 || c->schedule == 2) s.schedule = c->schedule;
   }
   return s;
 }
@@ -160,45 +162,45 @@ static int resolve_scrub_variant(int v) { return v == CCM_SCRUB_AUTO ? CCM_SCRUB
 static int resolve_verify_variant(int v) { return v == CCM_VERIFY_AUTO ? CCM_VERIFY_LD256 : v; }
 
 template <int VB, int UNROLL>
-static cudaError_t launch_scrub_st_pol(const RegionSplit& s, int grid, int threads, int pol, cudaStream_t st) {
+static cudaError_t launch_scrub_st_pol(const RegionSplit& s, int grid, int threads, int pol, Sched sc, cudaStream_t st) {
   switch (pol) {
-    case kPolEvictFirst: scrub_st_kernel<VB, UNROLL, kPolEvictFirst><<<grid, threads, 0, st>>>(s); break;
-    case kPolStreaming:  scrub_st_kernel<VB, UNROLL, kPolStreaming><<<grid, threads, 0, st>>>(s); break;
-    case kPolEvictLast:  scrub_st_kernel<VB, UNROLL, kPolEvictLast><<<grid, threads, 0, st>>>(s); break;
-    default:             scrub_st_kernel<VB, UNROLL, kPolDefault><<<grid, threads, 0, st>>>(s); break;
+    case kPolEvictFirst: scrub_st_kernel<VB, UNROLL, kPolEvictFirst><<<grid, threads, 0, st>>>(s, sc); break;
+    case kPolStreaming:  scrub_st_kernel<VB, UNROLL, kPolStreaming><<<grid, threads, 0, st>>>(s, sc); break;
+    case kPolEvictLast:  scrub_st_kernel<VB, UNROLL, kPolEvictLast><<<grid, threads, 0, st>>>(s, sc); break;
+    default:             scrub_st_kernel<VB, UNROLL, kPolDefault><<<grid, threads, 0, st>>>(s, sc); break;
   }
   return cudaGetLastError();
 }
 template <int VB>
-static cudaError_t launch_scrub_st(const RegionSplit& s, int grid, const Shape& sh, cudaStream_t st) {
+static cudaError_t launch_scrub_st(const RegionSplit& s, int grid, const Shape& sh, Sched sc, cudaStream_t st) {
   switch (sh.unroll) {
-    case 1: return launch_scrub_st_pol<VB, 1>(s, grid, sh.threads, sh.policy, st);
-    case 2: return launch_scrub_st_pol<VB, 2>(s, grid, sh.threads, sh.policy, st);
-    case 8: return launch_scrub_st_pol<VB, 8>(s, grid, sh.threads, sh.policy, st);
-    case 16: return launch_scrub_st_pol<VB, 16>(s, grid, sh.threads, sh.policy, st);
-    default: return launch_scrub_st_pol<VB, 4>(s, grid, sh.threads, sh.policy, st);
+    case 1: return launch_scrub_st_pol<VB, 1>(s, grid, sh.threads, sh.policy, sc, st);
+    case 2: return launch_scrub_st_pol<VB, 2>(s, grid, sh.threads, sh.policy, sc, st);
+    case 8: return launch_scrub_st_pol<VB, 8>(s, grid, sh.threads, sh.policy, sc, st);
+    case 16: return launch_scrub_st_pol<VB, 16>(s, grid, sh.threads, sh.policy, sc, st);
+    default: return launch_scrub_st_pol<VB, 4>(s, grid, sh.threads, sh.policy, sc, st);
   }
 }
 
 template <int VB, int UNROLL>
 static cudaError_t launch_verify_ld_pol(const RegionSplit& s, int grid, int threads, int pol,
-                                        unsigned long long* ctr, cudaStream_t st) {
+                                        unsigned long long* ctr, Sched sc, cudaStream_t st) {
   switch (pol) {
-    case kPolEvictFirst: verify_ld_kernel<VB, UNROLL, kPolEvictFirst><<<grid, threads, 0, st>>>(s, ctr); break;
-    case kPolStreaming:  verify_ld_kernel<VB, UNROLL, kPolStreaming><<<grid, threads, 0, st>>>(s, ctr); break;
-    case kPolEvictLast:  verify_ld_kernel<VB, UNROLL, kPolEvictLast><<<grid, threads, 0, st>>>(s, ctr); break;
-    default:             verify_ld_kernel<VB, UNROLL, kPolDefault><<<grid, threads, 0, st>>>(s, ctr); break;
+    case kPolEvictFirst: verify_ld_kernel<VB, UNROLL, kPolEvictFirst><<<grid, threads, 0, st>>>(s, ctr, sc); break;
+    case kPolStreaming:  verify_ld_kernel<VB, UNROLL, kPolStreaming><<<grid, threads, 0, st>>>(s, ctr, sc); break;
+    case kPolEvictLast:  verify_ld_kernel<VB, UNROLL, kPolEvictLast><<<grid, threads, 0, st>>>(s, ctr, sc); break;
+    default:             verify_ld_kernel<VB, UNROLL, kPolDefault><<<grid, threads, 0, st>>>(s, ctr, sc); break;
   }
   return cudaGetLastError();
 }
 template <int VB>
 static cudaError_t launch_verify_ld(const RegionSplit& s, int grid, const Shape& sh,
-                                    unsigned long long* ctr, cudaStream_t st) {
+                                    unsigned long long* ctr, Sched sc, cudaStream_t st) {
   switch (sh.unroll) {
-    case 1: return launch_verify_ld_pol<VB, 1>(s, grid, sh.threads, sh.policy, ctr, st);
-    case 2: return launch_verify_ld_pol<VB, 2>(s, grid, sh.threads, sh.policy, ctr, st);
-    case 8: return launch_verify_ld_pol<VB, 8>(s, grid, sh.threads, sh.policy, ctr, st);
-    default: return launch_verify_ld_pol<VB, 4>(s, grid, sh.threads, sh.policy, ctr, st);
+    case 1: return launch_verify_ld_pol<VB, 1>(s, grid, sh.threads, sh.policy, ctr, sc, st);
+    case 2: return launch_verify_ld_pol<VB, 2>(s, grid, sh.threads, sh.policy, ctr, sc, st);
+    case 8: return launch_verify_ld_pol<VB, 8>(s, grid, sh.threads, sh.policy, ctr, sc, st);
+    default: return launch_verify_ld_pol<VB, 4>(s, grid, sh.threads, sh.policy, ctr, sc, st);
   }
 }
 
@@ -206,6 +208,24 @@ static int clamp_threads(int t) {
   if (t < 32) t = 32;
   if (t > 1024) t = 1024;
   return (t / 32) * 32;
+}
+
+// Work-distribution descriptor for one launch.  Dynamic: the grab counter lives at
+// d_counter[8] (its own 64-byte line) and is zeroed on the launching stream first.
+static int make_sched(ScrubEngine* e, const Shape& sh, uint64_t tile_bytes, bool tma, cudaStream_t st, Sched* out) {
+  out->counter = nullptr;
+  out->chunk_tiles = 1;
+  if (sh.schedule != 2) return CCM_OK;
+  CCM_CUDA(cudaMemsetAsync(e->d_counter + 8, 0, sizeof(unsigned long long), st));
+  out->counter = e->d_counter + 8;
+  if (tma) {
+    out->chunk_tiles = sh.unroll > 0 ? (uint32_t)sh.unroll : 4;
+  } else {
+    const uint64_t chunk_bytes = sh.tile_bytes > 0 ? (uint64_t)sh.tile_bytes : 256 * 1024;
+    uint64_t ct = chunk_bytes / (tile_bytes ? tile_bytes : 1);
+    out->chunk_tiles = (uint32_t)(ct < 1 ? 1 : ct);
+  }
+  return CCM_OK;
 }
 
 // Scrub one contiguous range on `st` (no sync).
@@ -223,13 +243,17 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
       break;
     case CCM_SCRUB_ST128: {
       RegionSplit s = split_region(p, n, 16, 128);
-      err = launch_scrub_st<16>(s, grid, sh, st);
+      Sched sc;
+      if (int rc = make_sched(e, sh, (uint64_t)sh.threads * sh.unroll * 16, false, st, &sc)) return rc;
+      err = launch_scrub_st<16>(s, grid, sh, sc, st);
       g_launches++;
       break;
     }
     case CCM_SCRUB_ST256: {
       RegionSplit s = split_region(p, n, 32, 128);
-      err = launch_scrub_st<32>(s, grid, sh, st);
+      Sched sc;
+      if (int rc = make_sched(e, sh, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
+      err = launch_scrub_st<32>(s, grid, sh, sc, st);
       g_launches++;
       break;
     }
@@ -240,12 +264,13 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
       if (tile > e->smem_optin - 1024) tile = (uint32_t)((e->smem_optin - 1024) & ~127ull);
       const int threads = sh.threads > 256 ? 256 : sh.threads;
       const uint32_t ops_per_group = sh.unroll > 0 ? (uint32_t)sh.unroll : 4;
-      const uint32_t inflight = 0;  // unbounded: drain once at exit
+      Sched sc;
+      if (int rc = make_sched(e, sh, tile, true, st, &sc)) return rc;
 #define CCM_TMA_LAUNCH(POL)                                                                       \
       do {                                                                                        \
         err = cudaFuncSetAttribute(scrub_tma_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile); \
         if (err == cudaSuccess) {                                                                 \
-          scrub_tma_kernel<POL><<<grid, threads, tile, st>>>(s, tile, ops_per_group, inflight);   \
+          scrub_tma_kernel<POL><<<grid, threads, tile, st>>>(s, tile, ops_per_group, sc);         \
           err = cudaGetLastError();                                                               \
         }                                                                                         \
       } while (0)
@@ -279,12 +304,16 @@ static int verify_range(ScrubEngine* e, const void* p, uint64_t n, int variant, 
   switch (variant) {
     case CCM_VERIFY_LD128: {
       RegionSplit s = split_region(p, n, 16, 128);
-      err = launch_verify_ld<16>(s, grid, sh, e->d_counter, st);
+      Sched sc;
+      if (int rc = make_sched(e, sh, (uint64_t)sh.threads * sh.unroll * 16, false, st, &sc)) return rc;
+      err = launch_verify_ld<16>(s, grid, sh, e->d_counter, sc, st);
       break;
     }
     case CCM_VERIFY_LD256: {
       RegionSplit s = split_region(p, n, 32, 128);
-      err = launch_verify_ld<32>(s, grid, sh, e->d_counter, st);
+      Sched sc;
+      if (int rc = make_sched(e, sh, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
+      err = launch_verify_ld<32>(s, grid, sh, e->d_counter, sc, st);
       break;
     }
     case CCM_VERIFY_TMA: {

@@ -131,20 +131,60 @@ __host__ __device__ inline RegionSplit split_region(const void* p, uint64_t n, i
   return s;
 }
 
+// ------------------------------------------------------------ work distribution
+// Tiles are handed to the persistent CTAs either statically (grid-stride) or
+// DYNAMICALLY: a CTA grabs the next chunk of `chunk_tiles` consecutive tiles with
+// one atomicAdd on a device counter (zeroed by the host before the launch).  The
+// grab for chunk k+1 is issued before the stores of chunk k, so its latency is
+// hidden.  Why: an SM can push at most 32 B/clk into the crossbar (ncu:
+// l1tex__m_l1tex2xbar_write_bytes), the chip-wide store ceiling is therefore only
+// ~1.2x the HBM write ceiling, and SMs do not all drain at the same rate; with a
+// static split the slowest SM sets the kernel time (profiles/r1_scrub_st256.md).
+struct Sched {
+  unsigned long long* counter;  // nullptr = static grid-stride
+  uint32_t chunk_tiles;         // tiles per grab (dynamic only)
+};
+
 // ------------------------------------------------------------- scrub (stores)
 template <int VB, int UNROLL, int POL>
+__device__ __forceinline__ void scrub_tile(uint8_t* body, uint64_t tile, uint64_t tile_vecs,
+                                           uint64_t stride_bytes, uint64_t l2pol) {
+  uint8_t* p = body + (tile * tile_vecs + threadIdx.x) * VB;
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) st_zero<VB, POL>(p + u * stride_bytes, l2pol);
+}
+
+template <int VB, int UNROLL, int POL>
 __global__ void __launch_bounds__(1024)
-scrub_st_kernel(RegionSplit s) {
+scrub_st_kernel(RegionSplit s, Sched sched) {
   uint8_t* body = s.base + s.head;
   const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
   const uint64_t ntiles = s.body_vecs / tile_vecs;
   const uint64_t stride_bytes = (uint64_t)blockDim.x * VB;
   const uint64_t l2pol = make_l2_policy<POL>();
 
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    uint8_t* p = body + (tile * tile_vecs + threadIdx.x) * VB;
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) st_zero<VB, POL>(p + u * stride_bytes, l2pol);
+  if (sched.counter == nullptr) {
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      scrub_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
+  } else {
+    __shared__ unsigned long long s_chunk[2];
+    const uint64_t nchunks = (ntiles + sched.chunk_tiles - 1) / sched.chunk_tiles;
+    if (threadIdx.x == 0) s_chunk[0] = atomicAdd(sched.counter, 1ull);
+    __syncthreads();
+    int buf = 0;
+    for (;;) {
+      const uint64_t c = s_chunk[buf];
+      if (c >= nchunks) break;
+      unsigned long long nxt = 0;
+      if (threadIdx.x == 0) nxt = atomicAdd(sched.counter, 1ull);  // prefetch the next grab
+      const uint64_t t0 = c * sched.chunk_tiles;
+      const uint64_t t1 = t0 + sched.chunk_tiles < ntiles ? t0 + sched.chunk_tiles : ntiles;
+      for (uint64_t tile = t0; tile < t1; ++tile)
+        scrub_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
+      if (threadIdx.x == 0) s_chunk[buf ^ 1] = nxt;
+      __syncthreads();
+      buf ^= 1;
+    }
   }
   // remainder vectors (< one tile), spread over the grid
   for (uint64_t i = ntiles * tile_vecs + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,9 +204,18 @@ scrub_st_kernel(RegionSplit s) {
 // streams cp.async.bulk.global.shared::cta ops (SASS: UBLKCP.G.S) grid-strided
 // over the body and drains them once at exit.
 template <int POL>
+__device__ __forceinline__ void bulk_store(uint8_t* dst, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+  if constexpr (POL == kPolEvictFirst || POL == kPolEvictLast)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst), "r"(src_smem), "r"(bytes), "l"(policy) : "memory");
+  else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+
+template <int POL>
 __global__ void __launch_bounds__(256)
-scrub_tma_kernel(RegionSplit s /* VB = 16 */, uint32_t tile_bytes, uint32_t ops_per_group,
-                 uint32_t max_groups_in_flight) {
+scrub_tma_kernel(RegionSplit s /* VB = 16 */, uint32_t tile_bytes, uint32_t ops_per_group, Sched sched) {
   extern __shared__ __align__(128) uint8_t zero_tile[];
   for (uint32_t i = threadIdx.x; i < tile_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(zero_tile)[i] = make_uint4(0, 0, 0, 0);
@@ -179,44 +228,37 @@ scrub_tma_kernel(RegionSplit s /* VB = 16 */, uint32_t tile_bytes, uint32_t ops_
   const uint64_t ntiles = body_bytes / tile_bytes;
   const uint32_t last_bytes = (uint32_t)(body_bytes - ntiles * (uint64_t)tile_bytes);  // multiple of 16
 
-  // each WARP's lane 0 issues; warps interleave tiles so issue cost is spread.
+  // each WARP's lane 0 issues; warps take interleaved tiles / their own chunks.
   const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   if ((threadIdx.x & 31) == 0) {
     const uint32_t src = (uint32_t)__cvta_generic_to_shared(zero_tile);
-    uint64_t policy = 0;
-    if constexpr (POL == kPolEvictFirst)
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    if constexpr (POL == kPolEvictLast)
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    uint32_t in_group = 0;
-    const uint64_t first = (uint64_t)blockIdx.x * nwarps + warp;
-    const uint64_t step = (uint64_t)gridDim.x * nwarps;
-    for (uint64_t tile = first; tile < ntiles; tile += step) {
-      uint8_t* dst = body + tile * (uint64_t)tile_bytes;
-      if constexpr (POL == kPolEvictFirst || POL == kPolEvictLast)
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                     ::"l"(dst), "r"(src), "r"(tile_bytes), "l"(policy) : "memory");
-      else
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     ::"l"(dst), "r"(src), "r"(tile_bytes) : "memory");
-      if (++in_group == ops_per_group) {
-        in_group = 0;
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // bound the number of committed-but-unfinished groups
-        switch (max_groups_in_flight) {
-          case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
-          case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
-          case 4: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
-          case 8: asm volatile("cp.async.bulk.wait_group 8;" ::: "memory"); break;
-          default: break;  // unbounded: drain only at exit
+    const uint64_t policy = make_l2_policy<POL>();
+    if (sched.counter == nullptr) {
+      uint32_t in_group = 0;
+      const uint64_t first = (uint64_t)blockIdx.x * nwarps + warp;
+      const uint64_t step = (uint64_t)gridDim.x * nwarps;
+      for (uint64_t tile = first; tile < ntiles; tile += step) {
+        bulk_store<POL>(body + tile * (uint64_t)tile_bytes, src, tile_bytes, policy);
+        if (++in_group == ops_per_group) {
+          in_group = 0;
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
+    } else {
+      const uint64_t nchunks = (ntiles + sched.chunk_tiles - 1) / sched.chunk_tiles;
+      unsigned long long c = atomicAdd(sched.counter, 1ull);
+      while (c < nchunks) {
+        const unsigned long long nxt = atomicAdd(sched.counter, 1ull);
+        const uint64_t t0 = c * sched.chunk_tiles;
+        const uint64_t t1 = t0 + sched.chunk_tiles < ntiles ? t0 + sched.chunk_tiles : ntiles;
+        for (uint64_t tile = t0; tile < t1; ++tile)
+          bulk_store<POL>(body + tile * (uint64_t)tile_bytes, src, tile_bytes, policy);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        c = nxt;
+      }
     }
-    if (last_bytes && blockIdx.x == 0 && warp == 0) {
-      uint8_t* dst = body + ntiles * (uint64_t)tile_bytes;
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                   ::"l"(dst), "r"(src), "r"(last_bytes) : "memory");
-    }
+    if (last_bytes && blockIdx.x == 0 && warp == 0)
+      bulk_store<kPolDefault>(body + ntiles * (uint64_t)tile_bytes, src, last_bytes, 0);
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -253,8 +295,41 @@ __device__ __forceinline__ void block_accumulate(uint64_t cnt, unsigned long lon
 // thread).  The expected answer is "all zero", so the hot loop only ORs the words
 // together; the exact per-byte count runs on the (rare) batches whose OR != 0.
 template <int VB, int UNROLL, int POL>
+__device__ __forceinline__ uint32_t verify_tile(const uint8_t* body, uint64_t tile, uint64_t tile_vecs,
+                                                uint64_t stride_bytes, uint64_t l2pol) {
+  constexpr int W = VB / 4;
+  const uint8_t* p = body + (tile * tile_vecs + threadIdx.x) * VB;
+  uint32_t w[UNROLL][W];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    if constexpr (VB == 32) {
+      Vec32 v = ld32<POL>(p + u * stride_bytes);
+#pragma unroll
+      for (int k = 0; k < W; ++k) w[u][k] = v.w[k];
+    } else {
+      Vec16 v = ld16<POL>(p + u * stride_bytes, l2pol);
+#pragma unroll
+      for (int k = 0; k < W; ++k) w[u][k] = v.w[k];
+    }
+  }
+  uint32_t any = 0;
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+    for (int k = 0; k < W; ++k) any |= w[u][k];
+  uint32_t c = 0;
+  if (any != 0) {
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int k = 0; k < W; ++k) c += nonzero_bytes_in_word(w[u][k]);
+  }
+  return c;
+}
+
+template <int VB, int UNROLL, int POL>
 __global__ void __launch_bounds__(1024)
-verify_ld_kernel(RegionSplit s, unsigned long long* counter) {
+verify_ld_kernel(RegionSplit s, unsigned long long* counter, Sched sched) {
   const uint8_t* body = s.base + s.head;
   const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
   const uint64_t ntiles = s.body_vecs / tile_vecs;
@@ -264,33 +339,27 @@ verify_ld_kernel(RegionSplit s, unsigned long long* counter) {
   const uint64_t l2pol = make_l2_policy<POL>();
   (void)l2pol;
 
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint8_t* p = body + (tile * tile_vecs + threadIdx.x) * VB;
-    uint32_t w[UNROLL][W];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      if constexpr (VB == 32) {
-        Vec32 v = ld32<POL>(p + u * stride_bytes);
-#pragma unroll
-        for (int k = 0; k < W; ++k) w[u][k] = v.w[k];
-      } else {
-        Vec16 v = ld16<POL>(p + u * stride_bytes, l2pol);
-#pragma unroll
-        for (int k = 0; k < W; ++k) w[u][k] = v.w[k];
-      }
-    }
-    uint32_t any = 0;
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-      for (int k = 0; k < W; ++k) any |= w[u][k];
-    if (any != 0) {
-      uint32_t c = 0;
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-        for (int k = 0; k < W; ++k) c += nonzero_bytes_in_word(w[u][k]);
-      cnt += c;
+  if (sched.counter == nullptr) {
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      cnt += verify_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
+  } else {
+    __shared__ unsigned long long s_chunk[2];
+    const uint64_t nchunks = (ntiles + sched.chunk_tiles - 1) / sched.chunk_tiles;
+    if (threadIdx.x == 0) s_chunk[0] = atomicAdd(sched.counter, 1ull);
+    __syncthreads();
+    int buf = 0;
+    for (;;) {
+      const uint64_t c = s_chunk[buf];
+      if (c >= nchunks) break;
+      unsigned long long nxt = 0;
+      if (threadIdx.x == 0) nxt = atomicAdd(sched.counter, 1ull);
+      const uint64_t t0 = c * sched.chunk_tiles;
+      const uint64_t t1 = t0 + sched.chunk_tiles < ntiles ? t0 + sched.chunk_tiles : ntiles;
+      for (uint64_t tile = t0; tile < t1; ++tile)
+        cnt += verify_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
+      if (threadIdx.x == 0) s_chunk[buf ^ 1] = nxt;
+      __syncthreads();
+      buf ^= 1;
     }
   }
   for (uint64_t i = ntiles * tile_vecs + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
