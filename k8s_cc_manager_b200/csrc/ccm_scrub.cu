@@ -128,11 +128,12 @@ ScrubEngine* engine_for(int ordinal) {
 // ------------------------------------------------------------- launch shapes
 struct Shape { int ctas_per_sm, threads, unroll, policy, tile_bytes, schedule; };  // schedule: 1 static, 2 dynamic
 
-// Defaults; the numbers come from the sweeps recorded in profiles/ (DESIGN.md §5).
+// Defaults = winners of the round-1 sweeps on B200 (profiles/r1_sweep_schedule.md):
+// persistent CTAs + dynamic chunk grabs beat every static split by 10-20 %.
 static Shape scrub_shape(int variant, const ccm_launch_cfg* c) {
   Shape s;
-  if (variant == CCM_SCRUB_TMA) s = Shape{1, 128, 4, kPolDefault, 32768, 1};
-  else s = Shape{8, 256, 4, kPolDefault, 0, 1};
+  if (variant == CCM_SCRUB_TMA) s = Shape{1, 32, 1, kPolDefault, 65536, 2};
+  else s = Shape{1, 512, 4, kPolDefault, 131072, 2};
   if (c) {
     if (c->ctas_per_sm > 0) s.ctas_per_sm = c->ctas_per_sm;
     if (c->threads_per_cta > 0) s.threads = c->threads_per_cta;
@@ -146,7 +147,7 @@ static Shape scrub_shape(int variant, const ccm_launch_cfg* c) {
 static Shape verify_shape(int variant, const ccm_launch_cfg* c) {
   Shape s;
   if (variant == CCM_VERIFY_TMA) s = Shape{2, 288, 0, kPolDefault, 16384, 1};
-  else s = Shape{4, 512, 4, kPolStreaming, 0, 1};
+  else s = Shape{4, 256, 4, kPolStreaming, 131072, 2};
   if (c) {
     if (c->ctas_per_sm > 0) s.ctas_per_sm = c->ctas_per_sm;
     if (c->threads_per_cta > 0) s.threads = c->threads_per_cta;

@@ -49,6 +49,16 @@ CC_READY_STATE_LABEL = "nvidia.com/cc.ready.state"
 JOURNAL_ANNOTATION = "nvidia.com/cc-manager.paused-component-labels"
 
 POD_POLL_SECONDS = 2.0
+
+
+def _now() -> float:       # indirection points: tests swap these for a virtual clock
+    return time.time()
+
+
+def _pause(seconds: float) -> None:
+    time.sleep(seconds)
+
+
 _READY_FOR_STATE = {"on": "true", "ppcie": "true", "off": "false"}
 
 
@@ -132,8 +142,8 @@ def evict_gpu_operator_components(v1, node_name: str, operator_namespace: str,
     A wait that times out is logged and ignored (as in the reference); only a k8s API
     failure while writing the labels makes this return False.
     """
-    clock = clock or time.time
-    sleep = sleep or time.sleep
+    clock = clock or _now
+    sleep = sleep or _pause
     logger.info("Evicting GPU operator components by setting deployment labels to 'paused'")
     try:
         paused = {name: _maybe_set_paused(value) for name, value in current_labels.items()}

@@ -1,0 +1,109 @@
+/*
+ * scrub_oracle.c — CPU restatement of the HBM scrub-and-verify contract.
+ *
+ * ORACLE — TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load this.  The product
+ * (k8s_cc_manager_b200, libccm.so) never links, loads or calls it.
+ *
+ * What it restates: the reference has NO scrub (reference
+ * main.py:502-529 ends at verify-mode), so there is no reference arithmetic to
+ * follow.  The contract is the one BASELINE.json:north_star states and SURVEY.md
+ * §8a row S / §8c spell out:
+ *     scrub : every byte of the region becomes 0x00               (memset)
+ *     verify: nonzero_bytes = #{ i : buf[i] != 0 }, exact, as u64 (byte loop)
+ * Parity status: pinned against the independent numpy statement
+ * (oracle/scrub_oracle.py: np.count_nonzero) and the known-answer vectors in
+ * tests/golden/scrub_vectors.json (k = 0, 1, 7, 4096 injected bytes incl. first
+ * byte, last byte and a non-16-aligned offset — SURVEY.md §8d); there is no
+ * reference-side golden for it because the reference has no such function.
+ *
+ * The seeded sparse test pattern (ccm_oracle_pattern_word) restates, independently,
+ * the formula the device fill kernel uses (csrc/scrub_kernels.cuh: pattern_word) so
+ * the GPU count can be checked at sizes the host never materialises.
+ *
+ * The *_mt entry points split the buffer over pthreads: they are the "serial
+ * CPU-driven path" baseline (BASELINE.md B1 spirit) timed by bench.py.
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+
+API void ccm_oracle_scrub(uint8_t* buf, uint64_t n) { memset(buf, 0, (size_t)n); }
+
+/* Deliberately the plainest statement: one compare per byte. */
+API uint64_t ccm_oracle_count_nonzero(const uint8_t* buf, uint64_t n) {
+  uint64_t c = 0;
+  for (uint64_t i = 0; i < n; ++i) c += (buf[i] != 0);
+  return c;
+}
+
+static uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+/* 8-byte little-endian word j of the seeded pattern:
+ *   r = splitmix64(seed + j); 7 words out of 8 are zero ((r & 7) != 0);
+ *   otherwise byte b is kept iff bit (8+b) of r is set, and a kept byte is
+ *   ((r >> 3) | 0x01..01) >> 8b, i.e. never zero.                                  */
+API uint64_t ccm_oracle_pattern_word(uint64_t seed, uint64_t j) {
+  uint64_t r = splitmix64(seed + j);
+  if ((r & 7) != 0) return 0;
+  uint64_t keep = 0;
+  for (int b = 0; b < 8; ++b)
+    if ((r >> (8 + b)) & 1) keep |= 0xFFull << (8 * b);
+  return ((r >> 3) | 0x0101010101010101ull) & keep;
+}
+
+API void ccm_oracle_fill_pattern(uint8_t* buf, uint64_t nbytes, uint64_t seed, uint64_t word_index0) {
+  uint64_t nwords = nbytes / 8;
+  for (uint64_t j = 0; j < nwords; ++j) {
+    uint64_t w = ccm_oracle_pattern_word(seed, word_index0 + j);
+    memcpy(buf + 8 * j, &w, 8); /* host is little-endian, as is the GPU */
+  }
+  memset(buf + 8 * nwords, 0, (size_t)(nbytes - 8 * nwords));
+}
+
+/* Expected verify result for a pattern-filled region, without materialising it. */
+API uint64_t ccm_oracle_pattern_count(uint64_t nbytes, uint64_t seed, uint64_t word_index0) {
+  uint64_t nwords = nbytes / 8, c = 0;
+  for (uint64_t j = 0; j < nwords; ++j) {
+    uint64_t w = ccm_oracle_pattern_word(seed, word_index0 + j);
+    for (int b = 0; b < 8; ++b) c += ((w >> (8 * b)) & 0xFF) != 0;
+  }
+  return c;
+}
+
+/* ---- multi-threaded scrub + verify over a host buffer (CPU baseline) ---------- */
+typedef struct { uint8_t* p; uint64_t n; uint64_t nz; int do_scrub; int do_verify; } job_t;
+
+static void* worker(void* arg) {
+  job_t* j = (job_t*)arg;
+  if (j->do_scrub) ccm_oracle_scrub(j->p, j->n);
+  if (j->do_verify) j->nz = ccm_oracle_count_nonzero(j->p, j->n);
+  return NULL;
+}
+
+/* mode bit 0: scrub, bit 1: verify.  Returns the non-zero byte count (0 if no verify). */
+API uint64_t ccm_oracle_scrub_verify_mt(uint8_t* buf, uint64_t n, int threads, int mode) {
+  if (threads < 1) threads = 1;
+  if (threads > 1024) threads = 1024;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
+  job_t* jobs = (job_t*)malloc(sizeof(job_t) * (size_t)threads);
+  uint64_t per = (n / (uint64_t)threads + 63) & ~63ull, off = 0, total = 0;
+  for (int i = 0; i < threads; ++i) {
+    uint64_t len = off >= n ? 0 : (n - off < per || i == threads - 1 ? n - off : per);
+    jobs[i] = (job_t){buf + off, len, 0, mode & 1, (mode >> 1) & 1};
+    off += len;
+    pthread_create(&th[i], NULL, worker, &jobs[i]);
+  }
+  for (int i = 0; i < threads; ++i) { pthread_join(th[i], NULL); total += jobs[i].nz; }
+  free(th);
+  free(jobs);
+  return total;
+}
