@@ -387,16 +387,18 @@ int engine_arena_acquire(ScrubEngine* e, uint64_t bytes, ccm_arena_info* out) {
   // First choice: ONE contiguous virtual range.  Fall back to a segment list
   // (largest-first, halving) when HBM is fragmented.
   uint8_t* p = nullptr;
-  cudaError_t err = cudaMalloc(&p, want);
+  // CCM_ARENA_MAX_SEGMENT_MB forces the segmented path (tests / fragmented HBM drills).
+  const uint64_t max_seg = env_u64("CCM_ARENA_MAX_SEGMENT_MB", 0) * kMiB;
+  cudaError_t err = max_seg ? cudaErrorMemoryAllocation : cudaMalloc(&p, want);
   if (err == cudaSuccess) {
     e->segs.push_back({p, want});
     e->arena_bytes = want;
   } else {
     cudaGetLastError();
-    uint64_t got = 0, chunk = 16ull << 30;
-    while (got < want && chunk >= 64 * kMiB) {
+    uint64_t got = 0, chunk = max_seg ? max_seg : 16ull << 30;
+    const uint64_t min_chunk = max_seg && max_seg < 64 * kMiB ? max_seg : 64 * kMiB;
+    while (got < want && chunk >= min_chunk) {
       uint64_t ask = want - got < chunk ? want - got : chunk;
-      if (!want_max && ask < chunk && ask < 64 * kMiB) { /* small exact tail */ }
       err = cudaMalloc(&p, ask);
       if (err == cudaSuccess) { e->segs.push_back({p, ask}); got += ask; }
       else { cudaGetLastError(); chunk >>= 1; }
