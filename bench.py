@@ -1,0 +1,384 @@
+#!/usr/bin/env python3
+"""bench.py — HBM scrub-and-verify throughput of the CC-transition hot path on B200.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W      [--impl reference]
+  N>1 is launched by the driver as torchrun with one rank per GPU (NCCL is used ONLY
+  for the barrier and the max/sum of the timings: the path is per-GPU independent, no
+  data-path collective — SURVEY.md §8e).
+
+A "step" = one pass of the hot path over one region: the scrub kernel zero-fills
+every byte of the arena, then the verify kernel reads it back and counts non-zero
+bytes.  Workload = BASELINE.json configs[1]: one B200, all the HBM a CUDA context can
+map (~190.6 GB of 191.5 GB), poisoned with 0xA5 before the first step.
+
+  value   whole-job GB/s with the region resident in HBM: (bytes zeroed + bytes read
+          back) over all ranks / max-over-ranks CUDA-event time of the K steps.
+  e2e     the same metric through the public API a manager calls
+          (k8s_cc_manager_b200.devices.Gpu.scrub_and_verify): cold call that acquires
+          the arena (cudaMalloc of all free HBM), runs both kernels, reads the 8-byte
+          count back to the host and frees the arena.  The path has NO host-resident
+          input — it takes a device index — so h2d_bytes_per_step is 0 and
+          d2h_bytes_per_step is the 8-byte count.
+  roofline     scrub kernel (HBM write bound): R bytes / mean CUDA-event duration of the
+               scrub launches inside the timed region, vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline the oracle's C port (memset + byte-wise count) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "HBM scrub-and-verify throughput (bytes zeroed + bytes read back per second, whole job)"
+UNIT = "GB/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, read+write)"
+        except Exception:  # noqa: BLE001
+            pass
+    return FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clock sampler
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU during the timed region (NVML)."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reason_bits = [], 0
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.error = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # noqa: BLE001
+            self.error = f"nvml unavailable: {exc}"
+            return self
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def _run(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+            except Exception as exc:  # noqa: BLE001
+                self.error = str(exc)
+                return
+            self._stop.wait(self.period)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        reasons = [name for bit, name in self.REASONS.items() if self.reason_bits & bit and name != "gpu_idle"]
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": reasons, "samples": len(self.samples)}
+        if self.error:
+            out["error"] = self.error
+        return out
+
+
+# ------------------------------------------------------------------- CPU baseline
+def cpu_scrub_verify(sample_gib: float, budget_s: float, passes_max: int = 64):
+    """oracle/scrub_oracle.c (memset + byte-wise non-zero count) on the host cores.
+    This is the ONLY place bench.py executes oracle code, and only as the baseline."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import numpy as np
+    import scrub_oracle as SO
+
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nbytes = int(sample_gib * 2**30)
+    buf = np.empty(nbytes, dtype=np.uint8)
+    buf[:] = 0xA5                                      # first touch + poison (untimed)
+    assert SO.scrub_verify_mt_c(buf, threads, scrub=False) == nbytes
+    assert SO.scrub_verify_mt_c(buf, threads) == 0     # warm pass (untimed)
+    passes, t0 = 0, time.perf_counter()
+    while passes < passes_max:
+        nz = SO.scrub_verify_mt_c(buf, threads)
+        passes += 1
+        assert nz == 0
+        if time.perf_counter() - t0 >= budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": 2.0 * nbytes * passes / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample_gib:g} GiB host buffer x {passes} passes of memset + byte-wise count "
+                      f"on {threads} pthreads (oracle/scrub_oracle.c); the reference has no scrub to time",
+            "seconds": dt, "bytes_per_pass": nbytes, "passes": passes}
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU statement of the path on the host cores (the reference
+    itself has no implementation of it — SURVEY.md §0 — and no compilable sources for
+    an oracle/_ref, so this is the oracle port, kind='port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import numpy as np
+    import scrub_oracle as SO
+
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    nbytes = int(args.cpu_sample_gib * 2**30)
+    buf = np.empty(nbytes, dtype=np.uint8)
+    buf[:] = 0xA5
+    for _ in range(max(1, args.warmup)):
+        SO.scrub_verify_mt_c(buf, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        assert SO.scrub_verify_mt_c(buf, threads) == 0
+    dt = time.perf_counter() - t0
+    value = 2.0 * nbytes * args.steps / dt / 1e9
+    sample = (f"each step = memset + byte-wise count over a {args.cpu_sample_gib:g} GiB host buffer on "
+              f"{threads} pthreads (bounded sample of the {args.gpus}-GPU workload)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1] CPU statement: scrub + read-back verify of a host buffer", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------- our arm
+def check(rc, what):
+    from k8s_cc_manager_b200 import _native as N
+    if rc != 0:
+        raise RuntimeError(f"{what}: {N.strerror(rc)}: {N.last_error()}")
+
+
+def run_ours(args):
+    import torch
+
+    from k8s_cc_manager_b200 import _native as N
+    from k8s_cc_manager_b200 import devices as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scrub path has no host fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
+
+    L = N.lib()
+    check(L.ccm_init(N.BACKEND_CUDASIM), "ccm_init")
+    dev = local
+    sv = N.SCRUB_VARIANTS[args.scrub]
+    vv = N.VERIFY_VARIANTS[args.verify]
+
+    # ---- resident region: everything the context can map (or --gib) -------------------
+    ai = N.ArenaInfo()
+    check(L.ccm_arena_acquire(dev, int(args.gib * 2**30) if args.gib > 0 else 0, C.byref(ai)), "arena_acquire")
+    R = int(ai.bytes)
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+    nz = C.c_uint64()
+    check(L.ccm_arena_fill(dev, 0xA5, sptr), "poison")          # untimed: pre-scrub content
+    check(L.ccm_arena_verify(dev, vv, None, sptr, C.byref(nz), None), "verify poison")
+    if nz.value != R:
+        raise RuntimeError(f"poisoned arena must read back {R} non-zero bytes, got {nz.value}")
+
+    def step():
+        check(L.ccm_arena_scrub_verify_async(dev, sv, vv, None, None, sptr), "scrub_verify_async")
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    check(L.ccm_arena_fetch_count(dev, sptr, C.byref(nz)), "fetch_count")
+    if nz.value != 0:
+        raise RuntimeError(f"scrub left {nz.value} non-zero bytes")
+    L.ccm_arena_step_times(dev, 0, None, None, None)             # drop warm-up step events
+
+    # ---- timed region: exactly K steps, device-timed, max over ranks ------------------
+    sampler = ClockSampler(local).start()
+    launches0 = L.ccm_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = L.ccm_kernel_launches() - launches0
+    check(L.ccm_arena_fetch_count(dev, sptr, C.byref(nz)), "fetch_count")   # D2H of the step result
+    if nz.value != 0:
+        raise RuntimeError(f"verify found {nz.value} non-zero bytes inside the timed region")
+    s_ms, v_ms, nsteps = (C.c_float * 64)(), (C.c_float * 64)(), C.c_int()
+    check(L.ccm_arena_step_times(dev, 64, s_ms, v_ms, C.byref(nsteps)), "step_times")
+    scrub_ms = statistics.mean(s_ms[:nsteps.value]) if nsteps.value else float("nan")
+    verify_ms = statistics.mean(v_ms[:nsteps.value]) if nsteps.value else float("nan")
+    check(L.ccm_arena_release(dev), "arena_release")
+
+    ms = reduce(ms_local, "MAX")
+    total_bytes = reduce(float(R), "SUM")
+    total_launches = int(reduce(float(launches), "SUM"))
+    value = 2.0 * total_bytes * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- e2e: the public API, cold (acquire + kernels + D2H count + release) -----------
+    gpu = [d for d in D.find_gpus()[0] if d.is_gpu()][dev]
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    gpu.scrub_and_verify(int(args.gib * 2**30) if args.gib > 0 else 0)      # warm the allocator path once
+    barrier()
+    t0 = time.perf_counter()
+    reports = [gpu.scrub_and_verify(int(args.gib * 2**30) if args.gib > 0 else 0) for _ in range(e2e_steps)]
+    torch.cuda.synchronize()
+    e2e_local = time.perf_counter() - t0
+    barrier()
+    e2e_s = reduce(e2e_local, "MAX")
+    e2e_bytes = reduce(float(sum(r.bytes_scrubbed for r in reports)), "SUM")
+    e2e_value = 2.0 * e2e_bytes / e2e_s / 1e9
+    last = reports[-1]
+
+    # ---- node transition through the manager (N=1 only; registers + API simulated) ----
+    transition = None
+    if world == 1 and not args.no_transition:
+        transition = measure_transition(L, N)
+
+    peak, peak_src = measured_peak()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[1]: B200 off->on transition scrub over all mappable HBM, "
+                        "read-back verify all-zero (pre-scrub content: 0xA5 poison)",
+            "region_bytes_per_gpu": R, "coverage_of_device_total": R / ai.device_total_bytes,
+            "arena_segments": ai.segments, "scrub_variant": args.scrub, "verify_variant": args.verify,
+            "l2": "no flush needed: region (>=190 GB) is >1000x the 126 MB L2; every step re-streams it",
+            "parallelism": f"{world} independent GPU(s), one process per GPU, no data-path collective",
+        },
+        "per_gpu": {"scrub_gbs": R / scrub_ms / 1e6, "verify_gbs": R / verify_ms / 1e6,
+                    "scrub_ms": scrub_ms, "verify_ms": verify_ms, "step_gbs": 2.0 * R * args.steps / ms_local / 1e6},
+        "roofline": {"bound": "hbm", "kernel": "scrub_st_kernel (HBM write)", "achieved": R / scrub_ms / 1e6,
+                     "peak": peak, "unit": "GB/s", "frac": R / scrub_ms / 1e6 / peak, "traffic": None,
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": R, "note": "of measured" if "MEASURED" in peak_src else "of fallback"},
+        "roofline_verify": {"bound": "hbm", "kernel": "verify_ld_kernel (HBM read)", "achieved": R / verify_ms / 1e6,
+                            "peak": peak, "unit": "GB/s", "frac": R / verify_ms / 1e6 / peak,
+                            "algorithmic_bytes_per_launch": R},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                "steps": e2e_steps, "seconds_per_step": e2e_s / e2e_steps,
+                "breakdown_ms_last_step": {"acquire": last.ms_acquire, "scrub": last.ms_scrub,
+                                           "verify": last.ms_verify, "release": last.ms_release,
+                                           "total": last.ms_total},
+                "api": "k8s_cc_manager_b200.devices.Gpu.scrub_and_verify -> ccm_scrub_verify (C ABI)",
+                "note": "no host-resident input exists on this path; timed region covers arena acquire, "
+                        "both kernels, D2H of the 8-byte count, arena release"},
+        "gpu_launches": total_launches,
+        "clocks": clocks,
+    }
+    if transition:
+        line["transition"] = transition
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_scrub_verify(args.cpu_sample_gib, args.cpu_budget_s)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def measure_transition(L, N):
+    """BASELINE metric 1 on ONE GPU: wall-clock of CCManager.set_cc_mode('on') from 'off',
+    eviction-gated.  Simulated and reported as such: CC registers, reset/boot latency
+    (0 ms), the k8s API server (in-memory).  Real: the full-HBM scrub gate."""
+    sys.path.insert(0, str(ROOT / "tests" / "fakes"))
+    import logging
+
+    import kubernetes
+    logging.disable(logging.CRITICAL)
+    from k8s_cc_manager_b200 import manager
+    out = {}
+    try:
+        L.ccm_sim_set(-1, b"cc_mode", 0)
+        c = kubernetes.reset_cluster()
+        from k8s_cc_manager_b200.drain_gate import COMPONENT_LABELS
+        labels = {k: "true" for k in COMPONENT_LABELS}
+        c.add_node("bench-node", labels)
+        os.environ["EVICT_OPERATOR_COMPONENTS"] = "true"
+        mgr = manager.CCManager("bench-node", "on", True)
+        for mode in ("on", "devtools", "off"):
+            t0 = time.perf_counter()
+            okay = mgr.set_cc_mode(mode)
+            dt = time.perf_counter() - t0
+            reps = mgr.last_transition.get("scrub") or []
+            out[f"to_{mode}"] = {"ok": bool(okay), "wall_s": dt,
+                                 "state_label": c.labels("bench-node").get("nvidia.com/cc.mode.state"),
+                                 "phase_seconds": mgr.last_transition.get("phase_seconds"),
+                                 "scrubbed_bytes": [r.bytes_scrubbed for r in reps] if isinstance(reps, list) else reps}
+        out["simulated"] = ["CC mode registers (sim backend; the box's driver-bound GPUs cannot be reset)",
+                            "reset/boot latency = 0 ms", "kubernetes API (in-memory fake, 0 ms RTT)"]
+        out["real"] = ["full-HBM scrub-and-verify gate on the GPU"]
+    finally:
+        logging.disable(logging.NOTSET)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--gib", type=float, default=0.0, help="region per GPU in GiB (0 = all mappable HBM)")
+    ap.add_argument("--scrub", default="auto", choices=("auto", "st128", "st256", "tma", "memset"))
+    ap.add_argument("--verify", default="auto", choices=("auto", "ld128", "ld256", "tma"))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample-gib", type=float, default=8.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-transition", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -114,7 +114,7 @@ def verify_all_ways(lib, expect):
 
 
 def test_seeded_pattern_count_matches_oracle(lib, arena):
-    nbytes = (1 << 30) + 24
+    nbytes = (1 << 30) + 29          # 5 ragged bytes after the last whole 8-byte word
     ai = arena(nbytes)
     assert ai.bytes == nbytes
     seed = 20260921
@@ -123,13 +123,11 @@ def test_seeded_pattern_count_matches_oracle(lib, arena):
     assert want > 0
     verify_all_ways(lib, want)
     # bytes on the device are the oracle's bytes (spot windows incl. the ragged end)
-    for off in (0, 8 * 12345, nbytes - 4096 - 24):
-        got = np.zeros(4096 + (24 if off else 0), dtype=np.uint8)
+    for off, length in ((0, 4096), (8 * 12345, 4096), (nbytes - 4096 - 29, 4096 + 29)):
+        got = np.zeros(length, dtype=np.uint8)
         ok(lib.ccm_arena_read(0, off, got.ctypes.data, got.nbytes))
         exp = np.zeros_like(got)
-        SO.fill_pattern_c(exp, seed, off // 8)
-        if off + got.nbytes == nbytes:
-            exp[-(nbytes % 8 or 8):] = exp[-(nbytes % 8 or 8):] * (nbytes % 8 == 0)
+        SO.fill_pattern_c(exp, seed, off // 8)      # the oracle also leaves the ragged tail zero
         assert np.array_equal(got, exp), off
 
 
@@ -272,7 +270,6 @@ def test_region_api_on_torch_memory_matches_torch(lib):
         ok(lib.ccm_region_scrub(0, C.c_void_p(view.data_ptr()), view.numel(), sv, None, None, None))
         torch.cuda.synchronize()
         assert int(torch.count_nonzero(view)) == 0
-        assert t[:3].ne(0).any() or True
     # bytes outside the view were not touched by the last scrub
     t.fill_(9)
     ok(lib.ccm_region_scrub(0, C.c_void_p(view.data_ptr()), view.numel(), N.SCRUB_AUTO, None, None, None))
