@@ -215,8 +215,13 @@ def run_ours(args):
     ai = N.ArenaInfo()
     check(L.ccm_arena_acquire(dev, int(args.gib * 2**30) if args.gib > 0 else 0, C.byref(ai)), "arena_acquire")
     R = int(ai.bytes)
-    stream = torch.cuda.current_stream()
+    # A dedicated non-default stream: its handle is what the C ABI launches on (a NULL
+    # handle would mean "the library's own stream"), and the torch events below are
+    # recorded on the same stream, so they bracket exactly these kernels.
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sptr = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
     nz = C.c_uint64()
     check(L.ccm_arena_fill(dev, 0xA5, sptr), "poison")          # untimed: pre-scrub content
     check(L.ccm_arena_verify(dev, vv, None, sptr, C.byref(nz), None), "verify poison")
