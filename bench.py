@@ -180,6 +180,7 @@ def run_ours(args):
 
     from k8s_cc_manager_b200 import _native as N
     from k8s_cc_manager_b200 import devices as D
+    from k8s_cc_manager_b200.aggregate import aggregate_job
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -260,10 +261,8 @@ def run_ours(args):
     verify_ms = statistics.mean(v_ms[:nsteps.value]) if nsteps.value else float("nan")
     check(L.ccm_arena_release(dev), "arena_release")
 
-    ms = reduce(ms_local, "MAX")
-    total_bytes = reduce(float(R), "SUM")
-    total_launches = int(reduce(float(launches), "SUM"))
-    value = 2.0 * total_bytes * args.steps / (ms * 1e-3) / 1e9
+    agg = aggregate_job(dist, "cuda", region_bytes=R, steps=args.steps, elapsed_ms=ms_local, launches=launches)
+    ms, value, total_launches = agg["ms"], agg["value_gbs"], agg["launches"]
 
     # ---- e2e: the public API, cold (acquire + kernels + D2H count + release) -----------
     gpu = [d for d in D.find_gpus()[0] if d.is_gpu()][dev]
