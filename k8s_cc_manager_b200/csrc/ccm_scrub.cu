@@ -14,6 +14,7 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>  // driver-API TYPES only: entry points are resolved at run time (no -lcuda)
 #include <cuda_runtime.h>
 
 #include "ccm_internal.h"
@@ -569,6 +570,157 @@ int engine_arena_rw(ScrubEngine* e, uint64_t offset, void* host, uint64_t bytes,
   return CCM_OK;
 }
 
+// ------------------------------------------------------- VMM (driver API, lazy)
+// The product call maps HBM in chunks through the virtual-memory-management API so
+// that (a) the chunks sit in ONE contiguous virtual range (one verify launch) and (b)
+// the GPU scrubs chunk i while the host is still creating chunk i+1.  Entry points come from
+// cudaGetDriverEntryPoint, so libccm.so has no link-time dependency on libcuda and
+// still loads on a CPU-only box.  (profiles/r1_alloc_probe.log: cudaMalloc/cudaFree
+// of 190 GB cost 110-380 ms + 60 ms when called back to back; the kernels need 50 ms.)
+struct VmmApi {
+  bool ok = false;
+  CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+};
+
+static const VmmApi& vmm() {
+  static VmmApi api = [] {
+    VmmApi a;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult st;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess &&
+             st == cudaDriverEntryPointSuccess && *fn != nullptr;
+    };
+    a.ok = get("cuMemAddressReserve", (void**)&a.AddressReserve) && get("cuMemAddressFree", (void**)&a.AddressFree) &&
+           get("cuMemCreate", (void**)&a.Create) && get("cuMemRelease", (void**)&a.Release) &&
+           get("cuMemMap", (void**)&a.Map) && get("cuMemUnmap", (void**)&a.Unmap) &&
+           get("cuMemSetAccess", (void**)&a.SetAccess) &&
+           get("cuMemGetAllocationGranularity", (void**)&a.GetGranularity);
+    if (!a.ok) cudaGetLastError();
+    return a;
+  }();
+  return api;
+}
+
+struct VmmChunk { uint64_t off, bytes; CUmemGenericAllocationHandle handle; cudaEvent_t verified; };
+
+// Pipelined scrub-and-verify over freshly mapped HBM.  Returns CCM_ERR_UNSUPPORTED when
+// the VMM path cannot be used at all (caller falls back to the arena path).
+static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* r) {
+  const VmmApi& api = vmm();
+  if (!api.ok) return CCM_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> g(e->mu);
+  if (!e->segs.empty()) { set_error("arena already held on CUDA device %d", e->ordinal); return CCM_ERR_STATE; }
+  CCM_CUDA(cudaSetDevice(e->ordinal));
+  size_t fr = 0, tot = 0;
+  CCM_CUDA(cudaMemGetInfo(&fr, &tot));
+  r->device_total_bytes = tot;
+  CUmemAllocationProp prop;
+  memset(&prop, 0, sizeof prop);
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = e->ordinal;
+  size_t gran = 0;
+  if (api.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
+    return CCM_ERR_UNSUPPORTED;
+  const bool want_max = (bytes == 0);
+  const uint64_t reserve = env_u64("CCM_ARENA_RESERVE_MB", 256) * kMiB;
+  uint64_t want = want_max ? (fr > reserve ? fr - reserve : 0) : bytes;
+  // physical memory comes in `gran` units; an exact request is rounded UP and the
+  // surplus bytes are scrubbed too (harmless, and they are ours).
+  const uint64_t va_bytes = want_max ? want / gran * gran : (want + gran - 1) / gran * gran;
+  if (va_bytes == 0) { set_error("no free HBM to scrub (free=%zu)", fr); return CCM_ERR_NOMEM; }
+  uint64_t chunk = env_u64("CCM_VMM_CHUNK_MB", 16384) * kMiB / gran * gran;
+  if (chunk < gran) chunk = gran;
+
+  CUdeviceptr base = 0;
+  if (api.AddressReserve(&base, va_bytes, 0, 0, 0) != CUDA_SUCCESS) return CCM_ERR_UNSUPPORTED;
+  cudaStream_t st = e->stream;
+  std::vector<VmmChunk> chunks;
+  CUmemAccessDesc acc;
+  memset(&acc, 0, sizeof acc);
+  acc.location = prop.location;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  int rc = CCM_OK;
+  double host_acquire = 0, host_release = 0;
+  uint64_t off = 0;
+
+  // ---- phase A: map chunk i, enqueue its scrub, go on mapping chunk i+1 ----------
+  cudaEventRecord(e->ev[0], st);
+  while (off < va_bytes && rc == CCM_OK) {
+    uint64_t n = va_bytes - off < chunk ? va_bytes - off : chunk;
+    const double t0 = now_ms();
+    CUmemGenericAllocationHandle h;
+    CUresult cr = api.Create(&h, n, &prop, 0);
+    if (cr == CUDA_ERROR_OUT_OF_MEMORY && chunk > 64 * kMiB && chunk > gran) {
+      chunk = (chunk / 2) / gran * gran;  // fragmented / less free than reported: try smaller pieces
+      if (chunk < gran) chunk = gran;
+      continue;
+    }
+    if (cr == CUDA_ERROR_OUT_OF_MEMORY && want_max && off > 0) break;  // take what there is
+    if (cr != CUDA_SUCCESS) { set_error("cuMemCreate(%llu) failed: %d", (unsigned long long)n, (int)cr); rc = cr == CUDA_ERROR_OUT_OF_MEMORY ? CCM_ERR_NOMEM : CCM_ERR_CUDA; break; }
+    CUresult mr = api.Map(base + off, n, 0, h, 0);
+    if (mr == CUDA_SUCCESS) mr = api.SetAccess(base + off, n, &acc, 1);
+    if (mr != CUDA_SUCCESS) {
+      api.Release(h);
+      set_error("cuMemMap/cuMemSetAccess failed: %d", (int)mr);
+      rc = CCM_ERR_CUDA;
+      break;
+    }
+    host_acquire += now_ms() - t0;
+    chunks.push_back(VmmChunk{off, n, h, nullptr});
+    if (rc == CCM_OK) rc = scrub_range(e, (void*)(base + off), n, CCM_SCRUB_AUTO, nullptr, st);
+    off += n;
+  }
+  const uint64_t mapped = off;
+  cudaEventRecord(e->ev[1], st);
+
+  // ---- phase B: ONE verify launch over the contiguous range, then give it all back --
+  // (Unmapping chunk i while later chunks are still being verified was measured and
+  // rejected: cuMemUnmap under a running kernel costs 4-40 ms per chunk; after the
+  // stream has drained the whole teardown is ~60 ms for 190 GB.)
+  if (rc == CCM_OK) {
+    if (cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st) != cudaSuccess) rc = CCM_ERR_CUDA;
+    if (rc == CCM_OK) rc = verify_range(e, (const void*)base, mapped, CCM_VERIFY_AUTO, nullptr, st);
+    cudaEventRecord(e->ev[2], st);
+    if (rc == CCM_OK &&
+        cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = CCM_ERR_CUDA;
+  }
+  cudaError_t serr = cudaStreamSynchronize(st);  // nothing may still touch the mapping below
+  {
+    const double t0 = now_ms();
+    if (mapped) api.Unmap(base, mapped);
+    for (auto& c : chunks) {
+      api.Release(c.handle);
+      if (c.verified) cudaEventDestroy(c.verified);
+    }
+    api.AddressFree(base, va_bytes);
+    host_release = now_ms() - t0;
+  }
+  if (rc == CCM_OK && serr != cudaSuccess) { set_error("stream sync failed: %s", cudaGetErrorString(serr)); rc = CCM_ERR_CUDA; }
+  if (rc != CCM_OK) return rc;
+
+  float ms_s = 0, ms_v = 0;
+  cudaEventElapsedTime(&ms_s, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&ms_v, e->ev[1], e->ev[2]);
+  r->bytes_scrubbed = mapped;
+  r->segments = (int)chunks.size();
+  r->ms_acquire = host_acquire;   // host time inside create/map/set-access (overlapped with the scrub)
+  r->ms_release = host_release;   // unmap + release + address-free after the stream drained
+  r->ms_scrub = ms_s;             // first scrub launch .. last scrub done (includes waiting for mappings)
+  r->ms_verify = ms_v;
+  r->nonzero_bytes = (uint64_t)*e->h_counter;
+  if (!want_max && mapped < bytes) { set_error("mapped only %llu of %llu bytes", (unsigned long long)mapped, (unsigned long long)bytes); return CCM_ERR_NOMEM; }
+  return CCM_OK;
+}
+
 // --------------------------------------------------------------- product call
 int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* out) {
   const double t0 = now_ms();
@@ -578,26 +730,31 @@ int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* out) {
   r.sm_count = e->sm_count;
   r.scrub_variant = resolve_scrub_variant(CCM_SCRUB_AUTO);
   r.verify_variant = resolve_verify_variant(CCM_VERIFY_AUTO);
-  ccm_arena_info ai;
-  int rc = engine_arena_acquire(e, bytes, &ai);
-  if (rc == CCM_OK) {
-    r.ms_acquire = ai.ms_acquire;
-    r.bytes_scrubbed = ai.bytes;
-    r.device_total_bytes = ai.device_total_bytes;
-    r.segments = ai.segments;
-    float ms_s = 0, ms_v = 0;
-    uint64_t nz = 0;
-    rc = engine_arena_scrub(e, CCM_SCRUB_AUTO, nullptr, nullptr, &ms_s);
-    if (rc == CCM_OK) rc = engine_arena_verify(e, CCM_VERIFY_AUTO, nullptr, nullptr, &nz, &ms_v);
-    r.ms_scrub = ms_s;
-    r.ms_verify = ms_v;
-    r.nonzero_bytes = nz;
-    int rc2 = engine_arena_release(e, &r.ms_release);
-    if (rc == CCM_OK) rc = rc2;
-    if (rc == CCM_OK && nz != 0) {
-      set_error("scrub verify found %llu non-zero bytes on CUDA device %d", (unsigned long long)nz, e->ordinal);
-      rc = CCM_ERR_DIRTY;
+  int rc = CCM_ERR_UNSUPPORTED;
+  if (env_u64("CCM_PIPELINE", 1) != 0) rc = scrub_verify_pipelined(e, bytes, &r);
+  if (rc == CCM_ERR_UNSUPPORTED) {
+    // plain path: one cudaMalloc'ed arena, whole-arena scrub, whole-arena verify
+    ccm_arena_info ai;
+    rc = engine_arena_acquire(e, bytes, &ai);
+    if (rc == CCM_OK) {
+      r.ms_acquire = ai.ms_acquire;
+      r.bytes_scrubbed = ai.bytes;
+      r.device_total_bytes = ai.device_total_bytes;
+      r.segments = ai.segments;
+      float ms_s = 0, ms_v = 0;
+      uint64_t nz = 0;
+      rc = engine_arena_scrub(e, CCM_SCRUB_AUTO, nullptr, nullptr, &ms_s);
+      if (rc == CCM_OK) rc = engine_arena_verify(e, CCM_VERIFY_AUTO, nullptr, nullptr, &nz, &ms_v);
+      r.ms_scrub = ms_s;
+      r.ms_verify = ms_v;
+      r.nonzero_bytes = nz;
+      int rc2 = engine_arena_release(e, &r.ms_release);
+      if (rc == CCM_OK) rc = rc2;
     }
+  }
+  if (rc == CCM_OK && r.nonzero_bytes != 0) {
+    set_error("scrub verify found %llu non-zero bytes on CUDA device %d", (unsigned long long)r.nonzero_bytes, e->ordinal);
+    rc = CCM_ERR_DIRTY;
   }
   r.ms_total = now_ms() - t0;
   r.status = rc;
