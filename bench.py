@@ -206,6 +206,14 @@ def run_ours(args):
         dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
         return float(t.item())
 
+    if dist:
+        # NCCL allocates its communicator buffers lazily: touch every collective used below
+        # BEFORE the arena takes all free HBM, and leave it headroom.
+        barrier()
+        reduce(0.0, "MAX")
+        reduce(0.0, "SUM")
+        os.environ.setdefault("CCM_ARENA_RESERVE_MB", "1024")
+
     L = N.lib()
     check(L.ccm_init(N.BACKEND_CUDASIM), "ccm_init")
     dev = local

@@ -59,6 +59,40 @@ def new_concurrent(gpus, nbytes, reps):
     return best
 
 
+def resident_kernels(gpus, nbytes, reps=3):
+    """Kernel-only GB/s with the region resident (arena API), all GPUs concurrently from
+    one thread each: best-of-`reps` CUDA-event time of the scrub and of the verify launch."""
+    import threading
+    L = N.lib()
+    res = [None] * len(gpus)
+
+    def work(i, g):
+        ai = N.ArenaInfo()
+        rc = L.ccm_arena_acquire(g.index, nbytes, C.byref(ai))
+        assert rc == 0, N.last_error()
+        ms, nz = C.c_float(), C.c_uint64()
+        best_s = best_v = 1e30
+        for k in range(reps + 1):
+            assert L.ccm_arena_scrub(g.index, N.SCRUB_AUTO, None, None, C.byref(ms)) == 0, N.last_error()
+            if k:
+                best_s = min(best_s, ms.value)
+            assert L.ccm_arena_verify(g.index, N.VERIFY_AUTO, None, None, C.byref(nz), C.byref(ms)) == 0
+            assert nz.value == 0
+            if k:
+                best_v = min(best_v, ms.value)
+        L.ccm_arena_release(g.index)
+        res[i] = (ai.bytes / best_s / 1e6, ai.bytes / best_v / 1e6, ai.bytes)
+
+    th = [threading.Thread(target=work, args=(i, g)) for i, g in enumerate(gpus)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    s = [r[0] for r in res]
+    v = [r[1] for r in res]
+    return {"kernel_scrub_gbs_min_med_max": [min(s), statistics.median(s), max(s)],
+            "kernel_verify_gbs_min_med_max": [min(v), statistics.median(v), max(v)],
+            "kernel_scrub_gbs_sum": sum(s), "kernel_verify_gbs_sum": sum(v)}
+
+
 def b2_serial_library(n_gpus, nbytes):
     """GPUs one after another: cudaMemsetAsync + torch.count_nonzero (library-only path)."""
     import torch
@@ -68,19 +102,22 @@ def b2_serial_library(n_gpus, nbytes):
     for g in range(n_gpus):
         torch.cuda.set_device(g)
         free, _ = torch.cuda.mem_get_info(g)
-        want = nbytes if nbytes else (free - (1 << 30)) // (2 << 20) * (2 << 20)
+        want = nbytes if nbytes else (free - (4 << 30)) // (2 << 20) * (2 << 20)
         buf = torch.empty(want, dtype=torch.uint8, device=f"cuda:{g}")
         rc = L.ccm_region_scrub(g, C.c_void_p(buf.data_ptr()), want, N.SCRUB_MEMSET, None, None, None)
         assert rc == 0, N.last_error()
         torch.cuda.synchronize(g)
-        nz = int(torch.count_nonzero(buf))
+        nz = 0
+        step = 256 << 20  # torch.count_nonzero on uint8 materialises an 8x temporary
+        for off in range(0, want, step):
+            nz += int(torch.count_nonzero(buf[off:off + step]))
         assert nz == 0
         total += want
         del buf
         torch.cuda.empty_cache()
     dt = time.perf_counter() - t0
     return {"wall_ms": dt * 1e3, "bytes_total": total, "aggregate_e2e_gbs": 2.0 * total / dt / 1e9,
-            "what": "constructed baseline B2: serial per GPU, cudaMemsetAsync + torch.count_nonzero, torch allocator"}
+            "what": "constructed baseline B2: serial per GPU, cudaMemsetAsync + torch.count_nonzero (256 MiB slices), torch allocator"}
 
 
 def b1_serial_cpu_driven(n_gpus, sample_bytes):
@@ -97,6 +134,7 @@ def b1_serial_cpu_driven(n_gpus, sample_bytes):
         torch.cuda.set_device(g)
         buf = torch.empty(sample_bytes, dtype=torch.uint8, device=f"cuda:{g}")
         buf.fill_(0xA5)
+        torch.cuda.synchronize(g)  # the library launches on its own stream
         rc = L.ccm_region_scrub(g, C.c_void_p(buf.data_ptr()), sample_bytes, N.SCRUB_MEMSET, None, None, None)
         assert rc == 0, N.last_error()
         torch.cuda.synchronize(g)
@@ -177,9 +215,10 @@ def main():
             nbytes = int(gb * 1e9) // (2 << 20) * (2 << 20)
             row = new_concurrent(all_gpus[:n], nbytes, args.reps)
             row.update(n_gpus=n, region_gb=gb or "max")
+            row.update(resident_kernels(all_gpus[:n], nbytes))
             out["sweep"].append(row)
             print(json.dumps({k: row[k] for k in ("n_gpus", "region_gb", "wall_ms", "aggregate_e2e_gbs",
-                                                  "aggregate_kernel_gbs", "scrub_gbs_min_med_max")}), flush=True)
+                                                  "kernel_scrub_gbs_min_med_max", "kernel_verify_gbs_min_med_max")}), flush=True)
     if not args.skip_baselines:
         for n in counts:
             out["baselines"][f"B2_n{n}_max"] = b2_serial_library(n, 0)
