@@ -275,7 +275,8 @@ def run_ours(args):
     # ---- e2e: the public API, cold (acquire + kernels + D2H count + release) -----------
     gpu = [d for d in D.find_gpus()[0] if d.is_gpu()][dev]
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    gpu.scrub_and_verify(int(args.gib * 2**30) if args.gib > 0 else 0)      # warm the allocator path once
+    for _ in range(max(3, args.warmup)):                                     # same W as the kernel arm
+        gpu.scrub_and_verify(int(args.gib * 2**30) if args.gib > 0 else 0)
     barrier()
     t0 = time.perf_counter()
     reports = [gpu.scrub_and_verify(int(args.gib * 2**30) if args.gib > 0 else 0) for _ in range(e2e_steps)]
@@ -315,7 +316,8 @@ def run_ours(args):
                             "peak": peak, "unit": "GB/s", "frac": R / verify_ms / 1e6 / peak,
                             "algorithmic_bytes_per_launch": R},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
-                "steps": e2e_steps, "seconds_per_step": e2e_s / e2e_steps,
+                "steps": e2e_steps, "warmup": max(3, args.warmup), "seconds_per_step": e2e_s / e2e_steps,
+                "ms_total_each_step": [r.ms_total for r in reports],
                 "breakdown_ms_last_step": {"acquire": last.ms_acquire, "scrub": last.ms_scrub,
                                            "verify": last.ms_verify, "release": last.ms_release,
                                            "total": last.ms_total},

@@ -148,7 +148,7 @@ static Shape scrub_shape(int variant, const ccm_launch_cfg* c) {
 static Shape verify_shape(int variant, const ccm_launch_cfg* c) {
   Shape s;
   if (variant == CCM_VERIFY_TMA) s = Shape{2, 288, 0, kPolDefault, 16384, 1};
-  else s = Shape{4, 256, 4, kPolStreaming, 131072, 2};
+  else s = Shape{1, 1024, 4, kPolStreaming, 131072, 2};
   if (c) {
     if (c->ctas_per_sm > 0) s.ctas_per_sm = c->ctas_per_sm;
     if (c->threads_per_cta > 0) s.threads = c->threads_per_cta;
