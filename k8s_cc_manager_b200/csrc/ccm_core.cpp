@@ -299,6 +299,9 @@ static int check_fault(Device& d, uint32_t op, const char* what) {
   return CCM_OK;
 }
 static int check_booted(Device& d, const char* what) {
+  // a reset device comes back by itself once its boot time has elapsed; wait_for_boot
+  // only blocks until then (a later transition may find devices a failed one left behind)
+  if (!d.booted && Clock::now() >= d.boot_ready_at) d.booted = true;
   if (!d.booted) { set_error("%s on %s before wait_for_boot after a reset", what, d.info.bdf); return CCM_ERR_NOT_BOOTED; }
   return CCM_OK;
 }

@@ -34,18 +34,21 @@ def test_enumeration_shape(sim):
 
 
 def test_set_stages_reset_applies_wait_boots(sim):
+    sim_set(0, "boot_ms", 300)
     g = D.find_gpus()[0][0]
     assert g.query_cc_mode() == "off"
     g.set_cc_mode("on")
     assert g.query_cc_mode() == "off"          # staged only (main.py:455-459)
     g.reset_with_os()
-    with pytest.raises(D.GpuError) as e:        # not usable until wait_for_boot
+    with pytest.raises(D.GpuError) as e:        # not usable until it has booted
         g.query_cc_mode()
     assert e.value.status == N.ERR_NOT_BOOTED
     g.wait_for_boot()
     assert g.query_cc_mode() == "on"
-    g.set_cc_mode("devtools"); g.reset_with_os(); g.wait_for_boot()
-    assert g.query_cc_mode() == "devtools"
+    sim_set(0, "boot_ms", 0)
+    g.set_cc_mode("devtools"); g.reset_with_os()
+    assert g.query_cc_mode() == "devtools"     # boot time elapsed: the device is back on its own
+    g.wait_for_boot()
     assert sim_trace()[:3] == ["0000:1b:00.0 query_cc_mode off", "0000:1b:00.0 set_cc_mode on",
                                "0000:1b:00.0 query_cc_mode off"]
 
