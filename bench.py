@@ -294,6 +294,16 @@ def run_ours(args):
         transition = measure_transition(L, N)
 
     peak, peak_src = measured_peak()
+    # DRAM traffic per launch: from the committed ncu capture (never measured under this run),
+    # scaled to this run's region size.
+    traffic_s = traffic_v = None
+    try:
+        tr = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        k = R / tr["region_bytes"]
+        traffic_s = int(k * (tr["scrub_st_kernel"]["dram_bytes_read"] + tr["scrub_st_kernel"]["dram_bytes_write"]))
+        traffic_v = int(k * (tr["verify_ld_kernel"]["dram_bytes_read"] + tr["verify_ld_kernel"]["dram_bytes_write"]))
+    except Exception:  # noqa: BLE001
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -309,11 +319,12 @@ def run_ours(args):
         "per_gpu": {"scrub_gbs": R / scrub_ms / 1e6, "verify_gbs": R / verify_ms / 1e6,
                     "scrub_ms": scrub_ms, "verify_ms": verify_ms, "step_gbs": 2.0 * R * args.steps / ms_local / 1e6},
         "roofline": {"bound": "hbm", "kernel": "scrub_st_kernel (HBM write)", "achieved": R / scrub_ms / 1e6,
-                     "peak": peak, "unit": "GB/s", "frac": R / scrub_ms / 1e6 / peak, "traffic": None,
+                     "peak": peak, "unit": "GB/s", "frac": R / scrub_ms / 1e6 / peak, "traffic": traffic_s,
+                     "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write of one full-arena launch)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": R, "note": "of measured" if "MEASURED" in peak_src else "of fallback"},
         "roofline_verify": {"bound": "hbm", "kernel": "verify_ld_kernel (HBM read)", "achieved": R / verify_ms / 1e6,
-                            "peak": peak, "unit": "GB/s", "frac": R / verify_ms / 1e6 / peak,
+                            "peak": peak, "unit": "GB/s", "frac": R / verify_ms / 1e6 / peak, "traffic": traffic_v,
                             "algorithmic_bytes_per_launch": R},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
                 "steps": e2e_steps, "warmup": max(3, args.warmup), "seconds_per_step": e2e_s / e2e_steps,
