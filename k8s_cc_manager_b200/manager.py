@@ -121,6 +121,8 @@ class CCManager:
         self.journal_labels = env.get("CC_JOURNAL_COMPONENT_LABELS", "false").lower() == "true"
         self._device_source = device_source or _devices.find_gpus
         self._sleep = time.sleep
+        self._pool: Optional[ThreadPoolExecutor] = None
+        self._pool_size = 0
         self.last_transition: dict = {}
 
         if v1 is not None:
@@ -191,6 +193,17 @@ class CCManager:
     def _workers(self, n: int) -> int:
         return n if self.max_parallel <= 0 else max(1, min(n, self.max_parallel))
 
+    def _executor(self, n: int) -> ThreadPoolExecutor:
+        """One long-lived pool (a thread per device), grown on demand: creating a pool per
+        phase costs ~50 us per thread, which is visible next to micro-second register ops."""
+        want = self._workers(n)
+        if self._pool is None or self._pool_size < want:
+            if self._pool is not None:
+                self._pool.shutdown(wait=True)
+            self._pool = ThreadPoolExecutor(max_workers=want, thread_name_prefix="cc-dev")
+            self._pool_size = want
+        return self._pool
+
     def _fan_out(self, items: Sequence, fn: Callable, phase: str) -> list:
         """Run fn(item) for every item — concurrently unless CC_MAX_PARALLEL=1 — and
         join.  The error of the lowest-index failing item is re-raised after the
@@ -210,9 +223,7 @@ class CCManager:
                 except BaseException as exc:  # noqa: BLE001 - re-raised below
                     errors[i] = exc
 
-            with ThreadPoolExecutor(max_workers=self._workers(len(items)),
-                                    thread_name_prefix=f"cc-{phase}") as pool:
-                list(pool.map(run, range(len(items))))
+            list(self._executor(len(items)).map(run, range(len(items))))
             for exc in errors:
                 if exc is not None:
                     raise exc
@@ -231,9 +242,10 @@ class CCManager:
             except Exception as exc:  # noqa: BLE001
                 logger.error("Unexpected error getting CC mode on %s: %s", gpu.bdf, exc)
                 return False
-        if self._workers(len(gpus)) == 1:
-            return all(query(g) for g in gpus)  # short-circuits like the reference
-        return all(self._fan_out(gpus, query, "query"))
+        # Register reads are micro-seconds: fanning them out costs more than it saves
+        # (benchmarks/config1_get_only.py), so the get-only path stays serial and
+        # short-circuits exactly like the reference.
+        return all(query(g) for g in gpus)
 
     def ppcie_mode_is_set(self, devices: list) -> bool:
         """reference main.py:298-315."""
@@ -243,9 +255,7 @@ class CCManager:
             except Exception as exc:  # noqa: BLE001
                 logger.error("Unexpected error getting PPCIe mode on %s: %s", dev.bdf, exc)
                 return False
-        if self._workers(len(devices)) == 1:
-            return all(query(d) for d in devices)
-        return all(self._fan_out(devices, query, "query"))
+        return all(query(d) for d in devices)
 
     # ------------------------------------------------------------ public entry
     def set_cc_mode(self, mode: str) -> bool:
