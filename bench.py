@@ -288,6 +288,31 @@ def run_ours(args):
     e2e_value = 2.0 * e2e_bytes / e2e_s / 1e9
     last = reports[-1]
 
+    # ---- informational: the same kernels driven with a HOST buffer (ccm_host_roundtrip:
+    # H2D of dirty bytes, count, scrub, count, D2H of the zeroed bytes).  Not how a manager
+    # calls the path (it passes a device index, not a buffer) — reported so that a number
+    # with host<->device copies inside the timed region exists too.  PCIe-bound by nature.
+    host_rt = None
+    if not args.no_host_roundtrip:
+        hb = 1 << 30
+        pinned = torch.empty(hb, dtype=torch.uint8, pin_memory=True)
+        pre, post = C.c_uint64(), C.c_uint64()
+        times = []
+        for i in range(4):
+            pinned.fill_(0xA5)
+            t0 = time.perf_counter()
+            check(L.ccm_host_roundtrip(dev, C.c_void_p(pinned.data_ptr()), hb, 0, sv, vv, C.byref(pre), C.byref(post)),
+                  "host_roundtrip")
+            dt = time.perf_counter() - t0
+            if pre.value != hb or post.value != 0 or int(pinned[:4096].sum()) != 0:
+                raise RuntimeError("host round trip returned wrong counts/bytes")
+            if i:
+                times.append(dt)
+        host_rt = {"value": 2.0 * hb * len(times) / sum(times) / 1e9, "unit": UNIT, "h2d_bytes_per_step": hb,
+                   "d2h_bytes_per_step": hb + 16, "steps": len(times), "seconds_per_step": sum(times) / len(times),
+                   "api": "ccm_host_roundtrip (C ABI): pinned host buffer -> device -> count, scrub, count -> host",
+                   "note": "PCIe-bound; informational — the manager's call takes no host buffer"}
+
     # ---- node transition through the manager (N=1 only; registers + API simulated) ----
     transition = None
     if world == 1 and not args.no_transition:
@@ -338,6 +363,8 @@ def run_ours(args):
         "gpu_launches": total_launches,
         "clocks": clocks,
     }
+    if host_rt:
+        line["e2e_host_buffers"] = host_rt
     if transition:
         line["transition"] = transition
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -398,6 +425,7 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-transition", action="store_true")
+    ap.add_argument("--no-host-roundtrip", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
