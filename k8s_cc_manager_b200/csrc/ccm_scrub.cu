@@ -160,8 +160,25 @@ static Shape verify_shape(int variant, const ccm_launch_cfg* c) {
   return s;
 }
 
-static int resolve_scrub_variant(int v) { return v == CCM_SCRUB_AUTO ? CCM_SCRUB_ST256 : v; }
-static int resolve_verify_variant(int v) { return v == CCM_VERIFY_AUTO ? CCM_VERIFY_LD256 : v; }
+// AUTO = the fastest variant measured on B200 (profiles/README.md).  ST256 and TMA tie on
+// throughput (7 618 vs 7 607 GB/s); TMA draws ~5 % less board power (601 vs 631 W,
+// profiles/r1_power_probe.json), so a deployment that prefers joules can pin it with
+// CCM_SCRUB_VARIANT=tma (st128 | st256 | tma | memset; CCM_VERIFY_VARIANT=ld128 | ld256 | tma).
+static int env_variant(const char* name, const char* const* names, int n, int dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  for (int i = 0; i < n; ++i)
+    if (!strcmp(v, names[i])) return i + 1;
+  return dflt;
+}
+static int resolve_scrub_variant(int v) {
+  static const char* const names[] = {"st128", "st256", "tma", "memset"};
+  return v == CCM_SCRUB_AUTO ? env_variant("CCM_SCRUB_VARIANT", names, 4, CCM_SCRUB_ST256) : v;
+}
+static int resolve_verify_variant(int v) {
+  static const char* const names[] = {"ld128", "ld256", "tma"};
+  return v == CCM_VERIFY_AUTO ? env_variant("CCM_VERIFY_VARIANT", names, 3, CCM_VERIFY_LD256) : v;
+}
 
 template <int VB, int UNROLL>
 static cudaError_t launch_scrub_st_pol(const RegionSplit& s, int grid, int threads, int pol, Sched sc, cudaStream_t st) {
