@@ -108,7 +108,8 @@ static void apply_sim_env(Device& d) {
 
 static void build_sim(int n_gpus, int n_switches, bool bind_cuda) {
   g_devs.clear();
-  const int ncuda = bind_cuda ? cuda_device_count() : 0;
+  // CCM_SIM_BIND_CUDA=0: synthetic GPUs with NO CUDA device behind them (scrub must fail)
+  const int ncuda = (bind_cuda && env_long("CCM_SIM_BIND_CUDA", 1) != 0) ? cuda_device_count() : 0;
   for (int i = 0; i < n_gpus; ++i) {
     auto d = std::make_unique<Device>();
     d->info.index = (int)g_devs.size();
