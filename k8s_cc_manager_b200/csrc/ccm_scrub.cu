@@ -231,9 +231,12 @@ static int clamp_threads(int t) {
 
 // Work-distribution descriptor for one launch.  Dynamic: the grab counter lives at
 // d_counter[8] (its own 64-byte line) and is zeroed on the launching stream first.
-static int make_sched(ScrubEngine* e, const Shape& sh, uint64_t tile_bytes, bool tma, cudaStream_t st, Sched* out) {
+static int make_sched(ScrubEngine* e, const Shape& sh, uint64_t body_bytes, uint64_t tile_bytes, bool tma,
+                      cudaStream_t st, Sched* out) {
   out->counter = nullptr;
   out->chunk_tiles = 1;
+  out->ntiles = tile_bytes ? body_bytes / tile_bytes : 0;
+  out->nchunks = out->ntiles;
   if (sh.schedule != 2) return CCM_OK;
   CCM_CUDA(cudaMemsetAsync(e->d_counter + 8, 0, sizeof(unsigned long long), st));
   out->counter = e->d_counter + 8;
@@ -244,6 +247,7 @@ static int make_sched(ScrubEngine* e, const Shape& sh, uint64_t tile_bytes, bool
     uint64_t ct = chunk_bytes / (tile_bytes ? tile_bytes : 1);
     out->chunk_tiles = (uint32_t)(ct < 1 ? 1 : ct);
   }
+  out->nchunks = (out->ntiles + out->chunk_tiles - 1) / out->chunk_tiles;
   return CCM_OK;
 }
 
@@ -254,6 +258,8 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
   variant = resolve_scrub_variant(variant);
   Shape sh = scrub_shape(variant, cfg);
   sh.threads = clamp_threads(sh.threads);
+  // the host computes the tile count, so it must use the UNROLL that is actually instantiated
+  if (variant != CCM_SCRUB_TMA && sh.unroll != 1 && sh.unroll != 2 && sh.unroll != 8 && sh.unroll != 16) sh.unroll = 4;
   const int grid = e->sm_count * (sh.ctas_per_sm > 0 ? sh.ctas_per_sm : 1);
   cudaError_t err = cudaSuccess;
   switch (variant) {
@@ -263,7 +269,7 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
     case CCM_SCRUB_ST128: {
       RegionSplit s = split_region(p, n, 16, 128);
       Sched sc;
-      if (int rc = make_sched(e, sh, (uint64_t)sh.threads * sh.unroll * 16, false, st, &sc)) return rc;
+      if (int rc = make_sched(e, sh, s.body_vecs * 16, (uint64_t)sh.threads * sh.unroll * 16, false, st, &sc)) return rc;
       err = launch_scrub_st<16>(s, grid, sh, sc, st);
       g_launches++;
       break;
@@ -271,7 +277,7 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
     case CCM_SCRUB_ST256: {
       RegionSplit s = split_region(p, n, 32, 128);
       Sched sc;
-      if (int rc = make_sched(e, sh, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
+      if (int rc = make_sched(e, sh, s.body_vecs * 32, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
       err = launch_scrub_st<32>(s, grid, sh, sc, st);
       g_launches++;
       break;
@@ -284,7 +290,7 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
       const int threads = sh.threads > 256 ? 256 : sh.threads;
       const uint32_t ops_per_group = sh.unroll > 0 ? (uint32_t)sh.unroll : 4;
       Sched sc;
-      if (int rc = make_sched(e, sh, tile, true, st, &sc)) return rc;
+      if (int rc = make_sched(e, sh, s.body_vecs * 16, tile, true, st, &sc)) return rc;
 #define CCM_TMA_LAUNCH(POL)                                                                       \
       do {                                                                                        \
         err = cudaFuncSetAttribute(scrub_tma_kernel<POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile); \
@@ -318,20 +324,21 @@ static int verify_range(ScrubEngine* e, const void* p, uint64_t n, int variant, 
   variant = resolve_verify_variant(variant);
   Shape sh = verify_shape(variant, cfg);
   sh.threads = clamp_threads(sh.threads);
+  if (variant != CCM_VERIFY_TMA && sh.unroll != 1 && sh.unroll != 2 && sh.unroll != 8) sh.unroll = 4;
   const int grid = e->sm_count * (sh.ctas_per_sm > 0 ? sh.ctas_per_sm : 1);
   cudaError_t err = cudaSuccess;
   switch (variant) {
     case CCM_VERIFY_LD128: {
       RegionSplit s = split_region(p, n, 16, 128);
       Sched sc;
-      if (int rc = make_sched(e, sh, (uint64_t)sh.threads * sh.unroll * 16, false, st, &sc)) return rc;
+      if (int rc = make_sched(e, sh, s.body_vecs * 16, (uint64_t)sh.threads * sh.unroll * 16, false, st, &sc)) return rc;
       err = launch_verify_ld<16>(s, grid, sh, e->d_counter, sc, st);
       break;
     }
     case CCM_VERIFY_LD256: {
       RegionSplit s = split_region(p, n, 32, 128);
       Sched sc;
-      if (int rc = make_sched(e, sh, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
+      if (int rc = make_sched(e, sh, s.body_vecs * 32, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
       err = launch_verify_ld<32>(s, grid, sh, e->d_counter, sc, st);
       break;
     }

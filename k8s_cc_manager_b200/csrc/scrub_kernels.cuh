@@ -143,6 +143,8 @@ __host__ __device__ inline RegionSplit split_region(const void* p, uint64_t n, i
 struct Sched {
   unsigned long long* counter;  // nullptr = static grid-stride
   uint32_t chunk_tiles;         // tiles per grab (dynamic only)
+  uint64_t ntiles;              // whole tiles in the body   } computed on the host: no 64-bit
+  uint64_t nchunks;             // ceil(ntiles / chunk_tiles) } divides in the kernel prologue
 };
 
 // ------------------------------------------------------------- scrub (stores)
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(1024)
 scrub_st_kernel(RegionSplit s, Sched sched) {
   uint8_t* body = s.base + s.head;
   const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
-  const uint64_t ntiles = s.body_vecs / tile_vecs;
+  const uint64_t ntiles = sched.ntiles;
   const uint64_t stride_bytes = (uint64_t)blockDim.x * VB;
   const uint64_t l2pol = make_l2_policy<POL>();
 
@@ -168,7 +170,7 @@ scrub_st_kernel(RegionSplit s, Sched sched) {
       scrub_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
   } else {
     __shared__ unsigned long long s_chunk[2];
-    const uint64_t nchunks = (ntiles + sched.chunk_tiles - 1) / sched.chunk_tiles;
+    const uint64_t nchunks = sched.nchunks;
     if (threadIdx.x == 0) s_chunk[0] = atomicAdd(sched.counter, 1ull);
     __syncthreads();
     int buf = 0;
@@ -225,7 +227,7 @@ scrub_tma_kernel(RegionSplit s /* VB = 16 */, uint32_t tile_bytes, uint32_t ops_
 
   uint8_t* body = s.base + s.head;
   const uint64_t body_bytes = s.body_vecs * 16;
-  const uint64_t ntiles = body_bytes / tile_bytes;
+  const uint64_t ntiles = sched.ntiles;  // = body_bytes / tile_bytes
   const uint32_t last_bytes = (uint32_t)(body_bytes - ntiles * (uint64_t)tile_bytes);  // multiple of 16
 
   // each WARP's lane 0 issues; warps take interleaved tiles / their own chunks.
@@ -245,7 +247,7 @@ scrub_tma_kernel(RegionSplit s /* VB = 16 */, uint32_t tile_bytes, uint32_t ops_
         }
       }
     } else {
-      const uint64_t nchunks = (ntiles + sched.chunk_tiles - 1) / sched.chunk_tiles;
+      const uint64_t nchunks = sched.nchunks;
       unsigned long long c = atomicAdd(sched.counter, 1ull);
       while (c < nchunks) {
         const unsigned long long nxt = atomicAdd(sched.counter, 1ull);
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(1024)
 verify_ld_kernel(RegionSplit s, unsigned long long* counter, Sched sched) {
   const uint8_t* body = s.base + s.head;
   const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
-  const uint64_t ntiles = s.body_vecs / tile_vecs;
+  const uint64_t ntiles = sched.ntiles;
   const uint64_t stride_bytes = (uint64_t)blockDim.x * VB;
   constexpr int W = VB / 4;
   uint64_t cnt = 0;
@@ -344,7 +346,7 @@ verify_ld_kernel(RegionSplit s, unsigned long long* counter, Sched sched) {
       cnt += verify_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
   } else {
     __shared__ unsigned long long s_chunk[2];
-    const uint64_t nchunks = (ntiles + sched.chunk_tiles - 1) / sched.chunk_tiles;
+    const uint64_t nchunks = sched.nchunks;
     if (threadIdx.x == 0) s_chunk[0] = atomicAdd(sched.counter, 1ull);
     __syncthreads();
     int buf = 0;

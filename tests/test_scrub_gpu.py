@@ -163,6 +163,23 @@ def test_injected_nonzero_bytes_are_counted_exactly(lib, arena, k):
             assert nz.value == 0, (sv, cfg and cfg.schedule)
 
 
+def test_odd_launch_shapes_stay_exact(lib, arena):
+    """Unsupported unroll / thread / chunk values are normalised, never silently mis-tiled."""
+    nbytes = (192 << 20) + 77
+    arena(nbytes)
+    nz = C.c_uint64()
+    for unroll in (3, 5, 7, 16, 64):
+        for threads in (33, 100, 257, 4096):
+            for sched in (1, 2):
+                cfg = N.launch_cfg(ctas_per_sm=3, threads=threads, unroll=unroll, schedule=sched, tile_bytes=12345)
+                ok(lib.ccm_arena_fill(0, 0xA5, None))
+                ok(lib.ccm_arena_verify(0, N.VERIFY_LD256, C.byref(cfg), None, C.byref(nz), None))
+                assert nz.value == nbytes, (unroll, threads, sched)
+                ok(lib.ccm_arena_scrub(0, N.SCRUB_ST256, C.byref(cfg), None, None))
+                ok(lib.ccm_arena_verify(0, N.VERIFY_LD128, C.byref(cfg), None, C.byref(nz), None))
+                assert nz.value == 0, (unroll, threads, sched)
+
+
 def test_segmented_arena(lib, arena, monkeypatch):
     monkeypatch.setenv("CCM_ARENA_MAX_SEGMENT_MB", "96")
     ai = arena(300 << 20)
