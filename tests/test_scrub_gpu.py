@@ -320,3 +320,33 @@ def test_manager_transition_with_real_scrub_gate(lib, monkeypatch):
     assert mgr.set_cc_mode("off") is False
     assert c.labels("n")["nvidia.com/cc.mode.state"] == "failed"
     lib.ccm_sim_set(0, b"fail_op", 0)
+
+
+def test_multi_gpu_concurrent_gate(lib, monkeypatch):
+    """Needs >= 2 GPUs (skipped on a single-GPU box): every GPU scrubbed concurrently from one
+    process, independent contexts, no collective; manager transition over all of them."""
+    import kubernetes
+    from k8s_cc_manager_b200 import devices as D, manager
+    ok(lib.ccm_init(N.BACKEND_CUDASIM))
+    gpus = [d for d in D.find_gpus()[0] if d.is_gpu()]
+    if len(gpus) < 2:
+        pytest.skip("single-GPU box")
+    reports, wall_ms = D.scrub_and_verify_many(gpus, 0)
+    assert all(r.clean and r.coverage > 0.95 for r in reports)
+    assert len({r.bdf for r in reports}) == len(gpus)
+    # dirtying one GPU's memory is seen on that GPU only
+    ai = N.ArenaInfo()
+    ok(lib.ccm_arena_acquire(1, 1 << 30, C.byref(ai)))
+    ok(lib.ccm_arena_fill(1, 0x11, None))
+    nz = C.c_uint64()
+    ok(lib.ccm_arena_verify(1, N.VERIFY_AUTO, None, None, C.byref(nz), None))
+    assert nz.value == 1 << 30
+    ok(lib.ccm_arena_release(1))
+    lib.ccm_sim_set(-1, b"cc_mode", 0)
+    c = kubernetes.reset_cluster()
+    c.add_node("n", {})
+    monkeypatch.setenv("EVICT_OPERATOR_COMPONENTS", "false")
+    mgr = manager.CCManager("n", "on", True)
+    assert mgr.set_cc_mode("on") is True
+    assert len(mgr.last_transition["scrub"]) == len(gpus)
+    assert c.labels("n")["nvidia.com/cc.mode.state"] == "on"
