@@ -24,7 +24,9 @@
  *    Calls for the SAME device index are serialised by a per-device mutex.
  *  - `dev` is an index into the table returned by ccm_enumerate().
  *  - `stream` arguments are CUDA stream handles (cudaStream_t / CUstream) passed as
- *    void*; NULL means the library's own per-device stream.
+ *    void*; NULL means the library's own per-device stream.  Launches on ONE device
+ *    must be ordered with respect to each other (same stream, or event-ordered
+ *    streams): they share that device's result counter and tile-grab counter.
  */
 #ifndef CCM_H_
 #define CCM_H_
