@@ -189,3 +189,46 @@ def select_backend(name: str) -> None:
     if name not in N.BACKENDS:
         raise ValueError(f"unknown backend {name!r}")
     _check(N.lib().ccm_init(N.BACKENDS[name]), f"ccm_init({name})")
+
+
+class ScrubbingProxy:
+    """Wraps a device object from ANOTHER device library (e.g. the real gpu-admin-tools `Gpu`)
+    and adds the one capability it lacks: `scrub_and_verify()`, served by libccm.so on the CUDA
+    device with the same PCI address.  Every other attribute is forwarded untouched, so the
+    manager keeps using that library's register access for query/set/reset/wait_for_boot
+    (arrangement (1) of INTEGRATION.md §D)."""
+
+    def __init__(self, foreign, native: "NvidiaDevice | None"):
+        object.__setattr__(self, "_foreign", foreign)
+        object.__setattr__(self, "_native", native)
+
+    def __getattr__(self, name):
+        return getattr(object.__getattribute__(self, "_foreign"), name)
+
+    def __setattr__(self, name, value):
+        setattr(object.__getattribute__(self, "_foreign"), name, value)
+
+    def __repr__(self):
+        return f"<ScrubbingProxy {self._foreign!r} scrub={'libccm' if self._native else 'unavailable'}>"
+
+    def scrub_and_verify(self, nbytes: int = 0) -> ScrubReport:
+        native = object.__getattribute__(self, "_native")
+        if native is None:
+            raise GpuError(f"no CUDA device with PCI address {self._foreign.bdf}: HBM scrub cannot run", N.ERR_NO_CUDA)
+        return native.scrub_and_verify(nbytes)
+
+
+def _norm_bdf(bdf: str) -> str:
+    bdf = bdf.strip().lower()
+    return bdf if bdf.count(":") == 2 else "0000:" + bdf
+
+
+def with_scrub(foreign_find_gpus):
+    """Turns another library's `find_gpus()` into a device source for CCManager whose GPUs can be
+    scrubbed: `CCManager(..., device_source=with_scrub(pci.devices.find_gpus))`."""
+    def source():
+        devices, _ = foreign_find_gpus()
+        by_bdf = {_norm_bdf(d.bdf): d for d in find_gpus()[0] if d.is_gpu() and d.cuda_ordinal >= 0}
+        wrapped = [ScrubbingProxy(d, by_bdf.get(_norm_bdf(d.bdf))) if d.is_gpu() else d for d in devices]
+        return wrapped, len(wrapped)
+    return source

@@ -565,6 +565,22 @@ class CCManager:
         self.watch_and_apply()
 
 
+def _device_source_from_env():
+    """CC_DEVICE_LIBRARY=gpu-admin-tools: keep NVIDIA/gpu-admin-tools for the register work (it is
+    looked up where the reference looks, <app dir>/gpu-admin-tools, reference main.py:30-31) and
+    add only the HBM scrub from libccm.so, matched by PCI address.  Default: libccm.so for both."""
+    choice = os.environ.get("CC_DEVICE_LIBRARY", "libccm").lower()
+    if choice in ("", "libccm"):
+        return None
+    if choice != "gpu-admin-tools":
+        raise ValueError(f"CC_DEVICE_LIBRARY must be 'libccm' or 'gpu-admin-tools', not {choice!r}")
+    tools = os.environ.get("GPU_ADMIN_TOOLS_PATH") or os.path.join(
+        os.path.dirname(os.path.abspath(sys.argv[0] or ".")), "gpu-admin-tools")
+    sys.path.insert(0, tools)
+    from pci.devices import find_gpus as foreign_find_gpus  # noqa: PLC0415 - optional dependency
+    return _devices.with_scrub(foreign_find_gpus)
+
+
 def build_arg_parser() -> argparse.ArgumentParser:
     env = os.environ
     parser = argparse.ArgumentParser(description="NVIDIA CC Manager For Kubernetes (B200-native)")
@@ -601,7 +617,8 @@ def main(argv: Optional[List[str]] = None) -> None:
 
     try:
         CCManager(node_name=args.node_name, default_mode=default_mode, host_cc=host_cc,
-                  kubeconfig=args.kubeconfig, scrub_mode=args.scrub_mode).run()
+                  kubeconfig=args.kubeconfig, scrub_mode=args.scrub_mode,
+                  device_source=_device_source_from_env()).run()
     except KeyboardInterrupt:
         logger.info("Shutting down...")
         sys.exit(0)
