@@ -40,11 +40,13 @@ int main() {
     std::thread reader([&] {
       std::vector<ccm_dev_info> infos(64);
       std::vector<char> buf(1 << 20);
-      while (!stop) {
+      for (int it = 0; !stop; ++it) {
         int n = 0;
         CHECK(ccm_enumerate(infos.data(), 64, &n));
         if (n != G + 4) failures++;
-        ccm_sim_trace(buf.data(), buf.size());
+        if (it % 64 == 0) ccm_sim_trace(buf.data(), buf.size());   // copies + sorts the whole trace
+        if (it % 1024 == 1023) ccm_sim_trace_clear();
+        std::this_thread::yield();
       }
     });
     for (auto& t : th) t.join();
