@@ -18,7 +18,7 @@ for sv in (1, 2, 3):
             assert rc == 0 and pre.value == want and post.value == 0 and not host.any(), (sv, vv, nbytes, rc, N.last_error())
 ai = N.ArenaInfo(); assert L.ccm_arena_acquire(0, (96 << 20) + 48, C.byref(ai)) == 0
 nz = C.c_uint64()
-for sched in (1, 2):
+for sched in (1, 2, 3):
     for sv in (1, 2, 3):
         cfg = N.launch_cfg(schedule=sched)
         assert L.ccm_arena_fill(0, 0xA5, None) == 0

@@ -163,7 +163,8 @@ typedef struct ccm_launch_cfg {
   int32_t cache_policy; /* 0 library default, 1 plain, 2 L2::evict_first,
                            3 streaming (.cs / L1::no_allocate), 4 L2::evict_last */
   int32_t schedule;     /* 0 library default, 1 static grid-stride, 2 dynamic
-                           (persistent CTAs grab chunks off an atomic counter)  */
+                           (persistent CTAs grab chunks off an atomic counter),
+                           3 dynamic per WARP (ST/LD variants; no block barrier) */
 } ccm_launch_cfg;
 
 typedef struct ccm_scrub_result {

@@ -141,7 +141,7 @@ static Shape scrub_shape(int variant, const ccm_launch_cfg* c) {
     if (c->unroll > 0) s.unroll = c->unroll;
     if (c->cache_policy >= 1 && c->cache_policy <= 4) s.policy = c->cache_policy - 1;
     if (c->tile_bytes > 0) s.tile_bytes = c->tile_bytes;
-    if (c->schedule == 1 || c->schedule == 2) s.schedule = c->schedule;
+    if (c->schedule >= 1 && c->schedule <= 3) s.schedule = c->schedule;
   }
   return s;
 }
@@ -155,7 +155,7 @@ static Shape verify_shape(int variant, const ccm_launch_cfg* c) {
     if (c->unroll > 0) s.unroll = c->unroll;
     if (c->cache_policy >= 1 && c->cache_policy <= 4) s.policy = c->cache_policy - 1;
     if (c->tile_bytes > 0) s.tile_bytes = c->tile_bytes;
-    if (c->schedule == 1 || c->schedule == 2) s.schedule = c->schedule;
+    if (c->schedule >= 1 && c->schedule <= 3) s.schedule = c->schedule;
   }
   return s;
 }
@@ -235,9 +235,14 @@ static int make_sched(ScrubEngine* e, const Shape& sh, uint64_t body_bytes, uint
                       cudaStream_t st, Sched* out) {
   out->counter = nullptr;
   out->chunk_tiles = 1;
+  out->per_warp = 0;
+  if (sh.schedule == 3 && !tma) {  // warp-granular grabs: a tile is what ONE warp covers
+    out->per_warp = 1;
+    tile_bytes = tile_bytes / (uint64_t)sh.threads * 32;
+  }
   out->ntiles = tile_bytes ? body_bytes / tile_bytes : 0;
   out->nchunks = out->ntiles;
-  if (sh.schedule != 2) return CCM_OK;
+  if (sh.schedule != 2 && sh.schedule != 3) return CCM_OK;
   CCM_CUDA(cudaMemsetAsync(e->d_counter + 8, 0, sizeof(unsigned long long), st));
   out->counter = e->d_counter + 8;
   if (tma) {

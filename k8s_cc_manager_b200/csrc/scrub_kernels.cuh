@@ -145,13 +145,15 @@ struct Sched {
   uint32_t chunk_tiles;         // tiles per grab (dynamic only)
   uint64_t ntiles;              // whole tiles in the body   } computed on the host: no 64-bit
   uint64_t nchunks;             // ceil(ntiles / chunk_tiles) } divides in the kernel prologue
+  uint32_t per_warp;            // 1: every WARP grabs its own chunks (tile = 32 lanes x UNROLL vectors);
+                                //    no block barrier, no shared memory in the hot loop
 };
 
 // ------------------------------------------------------------- scrub (stores)
 template <int VB, int UNROLL, int POL>
-__device__ __forceinline__ void scrub_tile(uint8_t* body, uint64_t tile, uint64_t tile_vecs,
+__device__ __forceinline__ void scrub_tile(uint8_t* body, uint64_t tile, uint64_t tile_vecs, uint32_t idx,
                                            uint64_t stride_bytes, uint64_t l2pol) {
-  uint8_t* p = body + (tile * tile_vecs + threadIdx.x) * VB;
+  uint8_t* p = body + (tile * tile_vecs + idx) * VB;
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) st_zero<VB, POL>(p + u * stride_bytes, l2pol);
 }
@@ -160,14 +162,30 @@ template <int VB, int UNROLL, int POL>
 __global__ void __launch_bounds__(1024)
 scrub_st_kernel(RegionSplit s, Sched sched) {
   uint8_t* body = s.base + s.head;
-  const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
+  const uint32_t group = sched.per_warp ? 32u : blockDim.x;   // threads that share one tile
+  const uint32_t idx = sched.per_warp ? (threadIdx.x & 31u) : threadIdx.x;
+  const uint64_t tile_vecs = (uint64_t)group * UNROLL;
   const uint64_t ntiles = sched.ntiles;
-  const uint64_t stride_bytes = (uint64_t)blockDim.x * VB;
+  const uint64_t stride_bytes = (uint64_t)group * VB;
   const uint64_t l2pol = make_l2_policy<POL>();
 
   if (sched.counter == nullptr) {
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      scrub_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
+      scrub_tile<VB, UNROLL, POL>(body, tile, tile_vecs, idx, stride_bytes, l2pol);
+  } else if (sched.per_warp) {
+    const uint64_t nchunks = sched.nchunks;
+    unsigned long long c = 0;
+    if (idx == 0) c = atomicAdd(sched.counter, 1ull);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    while (c < nchunks) {
+      unsigned long long nxt = 0;
+      if (idx == 0) nxt = atomicAdd(sched.counter, 1ull);  // prefetch the next grab
+      const uint64_t t0 = c * sched.chunk_tiles;
+      const uint64_t t1 = t0 + sched.chunk_tiles < ntiles ? t0 + sched.chunk_tiles : ntiles;
+      for (uint64_t tile = t0; tile < t1; ++tile)
+        scrub_tile<VB, UNROLL, POL>(body, tile, tile_vecs, idx, stride_bytes, l2pol);
+      c = __shfl_sync(0xffffffffu, nxt, 0);
+    }
   } else {
     __shared__ unsigned long long s_chunk[2];
     const uint64_t nchunks = sched.nchunks;
@@ -182,7 +200,7 @@ scrub_st_kernel(RegionSplit s, Sched sched) {
       const uint64_t t0 = c * sched.chunk_tiles;
       const uint64_t t1 = t0 + sched.chunk_tiles < ntiles ? t0 + sched.chunk_tiles : ntiles;
       for (uint64_t tile = t0; tile < t1; ++tile)
-        scrub_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
+        scrub_tile<VB, UNROLL, POL>(body, tile, tile_vecs, idx, stride_bytes, l2pol);
       if (threadIdx.x == 0) s_chunk[buf ^ 1] = nxt;
       __syncthreads();
       buf ^= 1;
@@ -297,10 +315,10 @@ __device__ __forceinline__ void block_accumulate(uint64_t cnt, unsigned long lon
 // thread).  The expected answer is "all zero", so the hot loop only ORs the words
 // together; the exact per-byte count runs on the (rare) batches whose OR != 0.
 template <int VB, int UNROLL, int POL>
-__device__ __forceinline__ uint32_t verify_tile(const uint8_t* body, uint64_t tile, uint64_t tile_vecs,
+__device__ __forceinline__ uint32_t verify_tile(const uint8_t* body, uint64_t tile, uint64_t tile_vecs, uint32_t idx,
                                                 uint64_t stride_bytes, uint64_t l2pol) {
   constexpr int W = VB / 4;
-  const uint8_t* p = body + (tile * tile_vecs + threadIdx.x) * VB;
+  const uint8_t* p = body + (tile * tile_vecs + idx) * VB;
   uint32_t w[UNROLL][W];
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
@@ -333,9 +351,11 @@ template <int VB, int UNROLL, int POL>
 __global__ void __launch_bounds__(1024)
 verify_ld_kernel(RegionSplit s, unsigned long long* counter, Sched sched) {
   const uint8_t* body = s.base + s.head;
-  const uint64_t tile_vecs = (uint64_t)blockDim.x * UNROLL;
+  const uint32_t group = sched.per_warp ? 32u : blockDim.x;
+  const uint32_t idx = sched.per_warp ? (threadIdx.x & 31u) : threadIdx.x;
+  const uint64_t tile_vecs = (uint64_t)group * UNROLL;
   const uint64_t ntiles = sched.ntiles;
-  const uint64_t stride_bytes = (uint64_t)blockDim.x * VB;
+  const uint64_t stride_bytes = (uint64_t)group * VB;
   constexpr int W = VB / 4;
   uint64_t cnt = 0;
   const uint64_t l2pol = make_l2_policy<POL>();
@@ -343,7 +363,21 @@ verify_ld_kernel(RegionSplit s, unsigned long long* counter, Sched sched) {
 
   if (sched.counter == nullptr) {
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-      cnt += verify_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
+      cnt += verify_tile<VB, UNROLL, POL>(body, tile, tile_vecs, idx, stride_bytes, l2pol);
+  } else if (sched.per_warp) {
+    const uint64_t nchunks = sched.nchunks;
+    unsigned long long c = 0;
+    if (idx == 0) c = atomicAdd(sched.counter, 1ull);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    while (c < nchunks) {
+      unsigned long long nxt = 0;
+      if (idx == 0) nxt = atomicAdd(sched.counter, 1ull);
+      const uint64_t t0 = c * sched.chunk_tiles;
+      const uint64_t t1 = t0 + sched.chunk_tiles < ntiles ? t0 + sched.chunk_tiles : ntiles;
+      for (uint64_t tile = t0; tile < t1; ++tile)
+        cnt += verify_tile<VB, UNROLL, POL>(body, tile, tile_vecs, idx, stride_bytes, l2pol);
+      c = __shfl_sync(0xffffffffu, nxt, 0);
+    }
   } else {
     __shared__ unsigned long long s_chunk[2];
     const uint64_t nchunks = sched.nchunks;
@@ -358,7 +392,7 @@ verify_ld_kernel(RegionSplit s, unsigned long long* counter, Sched sched) {
       const uint64_t t0 = c * sched.chunk_tiles;
       const uint64_t t1 = t0 + sched.chunk_tiles < ntiles ? t0 + sched.chunk_tiles : ntiles;
       for (uint64_t tile = t0; tile < t1; ++tile)
-        cnt += verify_tile<VB, UNROLL, POL>(body, tile, tile_vecs, stride_bytes, l2pol);
+        cnt += verify_tile<VB, UNROLL, POL>(body, tile, tile_vecs, idx, stride_bytes, l2pol);
       if (threadIdx.x == 0) s_chunk[buf ^ 1] = nxt;
       __syncthreads();
       buf ^= 1;

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 VECTORS = json.loads((Path(__file__).parent / "golden" / "scrub_vectors.json").read_text())
 SCRUBS = [N.SCRUB_ST128, N.SCRUB_ST256, N.SCRUB_TMA, N.SCRUB_MEMSET]
 VERIFIES = [N.VERIFY_LD128, N.VERIFY_LD256, N.VERIFY_TMA]
-SCHEDULES = [1, 2]  # static grid-stride, dynamic chunk grabs
+SCHEDULES = [1, 2, 3]  # static grid-stride, dynamic chunk grabs per CTA, per warp
 
 
 def ok(rc, what=""):
@@ -170,7 +170,7 @@ def test_odd_launch_shapes_stay_exact(lib, arena):
     nz = C.c_uint64()
     for unroll in (3, 5, 7, 16, 64):
         for threads in (33, 100, 257, 4096):
-            for sched in (1, 2):
+            for sched in (1, 2, 3):
                 cfg = N.launch_cfg(ctas_per_sm=3, threads=threads, unroll=unroll, schedule=sched, tile_bytes=12345)
                 ok(lib.ccm_arena_fill(0, 0xA5, None))
                 ok(lib.ccm_arena_verify(0, N.VERIFY_LD256, C.byref(cfg), None, C.byref(nz), None))
