@@ -393,6 +393,9 @@ def measure_transition(L, N):
         labels = {k: "true" for k in COMPONENT_LABELS}
         c.add_node("bench-node", labels)
         os.environ["EVICT_OPERATOR_COMPONENTS"] = "true"
+        # this process shares its CUDA context with torch: do not reset it after the gate (a
+        # daemon does — CC_RELEASE_CUDA_CONTEXT=true — and then pays context creation per transition)
+        os.environ["CC_RELEASE_CUDA_CONTEXT"] = "false"
         mgr = manager.CCManager("bench-node", "on", True)
         for mode in ("on", "devtools", "off"):
             t0 = time.perf_counter()

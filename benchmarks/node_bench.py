@@ -168,6 +168,7 @@ def node_transition(n_gpus, max_parallel, reset_ms, boot_ms):
     c = kubernetes.reset_cluster()
     c.add_node("node", {k: "true" for k in COMPONENT_LABELS})
     os.environ["EVICT_OPERATOR_COMPONENTS"] = "true"
+    os.environ.setdefault("CC_RELEASE_CUDA_CONTEXT", "false")   # contexts are shared with the sweep in this process
     devs = D.find_gpus()[0][:n_gpus]
     mgr = manager.CCManager("node", "on", True, max_parallel=max_parallel, device_source=lambda: (devs, len(devs)))
     out = {}

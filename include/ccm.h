@@ -244,6 +244,14 @@ int ccm_host_roundtrip(int cuda_ordinal, void* host_buf, uint64_t bytes, uint64_
                        int scrub_variant, int verify_variant,
                        uint64_t* pre_nonzero, uint64_t* post_nonzero);
 
+/* Drops everything the library holds on the CUDA device behind `dev` — arena, stream, events,
+ * counters — and resets that device's primary context (cudaDeviceReset).  A daemon must not sit
+ * on a CUDA context between transitions: the context pins ~0.5 GB of HBM, keeps the GPU "in use"
+ * (it cannot be unbound for vfio) and does not survive the device reset of the next transition
+ * (reference main.py:519).  The next scrub call re-creates what it needs.  The sysfs backend
+ * calls this implicitly before it resets a device.  No-op (CCM_OK) when nothing is held. */
+int ccm_device_release(int dev);
+
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t ccm_kernel_launches(void);
 

@@ -138,6 +138,7 @@ _SIGNATURES = {
     "ccm_region_scrub": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_int, _P(LaunchCfg), C.c_void_p, _P(C.c_float)]),
     "ccm_region_verify": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_int, _P(LaunchCfg), C.c_void_p, _P(C.c_uint64), _P(C.c_float)]),
     "ccm_host_roundtrip": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _P(C.c_uint64), _P(C.c_uint64)]),
+    "ccm_device_release": (C.c_int, [C.c_int]),
     "ccm_kernel_launches": (C.c_uint64, []),
     "ccm_sim_topology": (C.c_int, [C.c_int, C.c_int]),
     "ccm_sim_set": (C.c_int, [C.c_int, C.c_char_p, C.c_int64]),

@@ -348,6 +348,8 @@ static int op_set_ppcie(Device& d, int mode) {
 }
 static int op_reset(Device& d) {
   if (g_backend == CCM_BACKEND_SYSFS) {
+    // a CUDA context must not be alive on a function that is about to be reset
+    if (d.info.cuda_ordinal >= 0) engine_teardown(d.info.cuda_ordinal);
     std::ofstream f(d.sysfs_path + "/reset");
     if (!f) { set_error("cannot open %s/reset", d.sysfs_path.c_str()); return CCM_ERR_IO; }
     f << "1";
@@ -623,6 +625,13 @@ int ccm_host_roundtrip(int cuda_ordinal, void* host_buf, uint64_t bytes, uint64_
   if (bytes && !host_buf) return CCM_ERR_INVALID;
   int rc; ScrubEngine* e = engine_of_ordinal(cuda_ordinal, &rc);
   return e ? engine_host_roundtrip(e, host_buf, bytes, dev_offset, sv, vv, pre, post) : rc;
+}
+
+int ccm_device_release(int dev) {
+  int ord = -1;
+  int rc = with_dev(dev, [&](Device& d) { ord = d.info.cuda_ordinal; return (int)CCM_OK; });
+  if (rc) return rc;
+  return ord >= 0 ? engine_teardown(ord) : (int)CCM_OK;
 }
 
 uint64_t ccm_kernel_launches(void) { return kernel_launches(); }

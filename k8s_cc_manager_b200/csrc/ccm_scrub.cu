@@ -72,7 +72,7 @@ struct ScrubEngine {
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;   // the engine's own non-blocking stream
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t step_ev[kMaxSteps][3];
+  cudaEvent_t step_ev[kMaxSteps][3] = {};
   int step_count = 0;
   unsigned long long* d_counter = nullptr;
   unsigned long long* h_counter = nullptr;  // pinned
@@ -124,6 +124,34 @@ ScrubEngine* engine_for(int ordinal) {
   std::lock_guard<std::mutex> g(e->mu);
   if (e->init() != CCM_OK) return nullptr;
   return e;
+}
+
+int engine_teardown(int ordinal) {
+  ScrubEngine* e = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_engines_mu);
+    if (ordinal < 0 || (size_t)ordinal >= g_engines.size()) return CCM_OK;  // never created: nothing held
+    e = g_engines[ordinal].get();
+  }
+  std::lock_guard<std::mutex> g(e->mu);
+  if (!e->ready) return CCM_OK;
+  CCM_CUDA(cudaSetDevice(ordinal));
+  cudaStreamSynchronize(e->stream);
+  for (auto& s : e->segs) cudaFree(s.ptr);
+  e->segs.clear();
+  e->arena_bytes = 0;
+  for (auto& ev : e->ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+  for (auto& st : e->step_ev) for (auto& ev : st) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+  e->step_count = 0;
+  if (e->d_counter) cudaFree(e->d_counter);
+  if (e->h_counter) cudaFreeHost(e->h_counter);
+  e->d_counter = nullptr;
+  e->h_counter = nullptr;
+  if (e->stream) cudaStreamDestroy(e->stream);
+  e->stream = nullptr;
+  e->ready = false;
+  CCM_CUDA(cudaDeviceReset());  // destroys the primary context of the current device
+  return CCM_OK;
 }
 
 // ------------------------------------------------------------- launch shapes

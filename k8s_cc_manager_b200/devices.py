@@ -143,6 +143,12 @@ class NvidiaDevice:
         return ScrubReport.from_native(self.bdf, res)
 
 
+    def release_cuda_context(self) -> None:
+        """Give back everything libccm holds on this GPU, including its CUDA primary context
+        (include/ccm.h: ccm_device_release).  Call it when the scrub gate is done."""
+        _check(N.lib().ccm_device_release(self.index), "release_cuda_context", self.bdf)
+
+
 class Gpu(NvidiaDevice):
     pass
 
@@ -210,6 +216,11 @@ class ScrubbingProxy:
 
     def __repr__(self):
         return f"<ScrubbingProxy {self._foreign!r} scrub={'libccm' if self._native else 'unavailable'}>"
+
+    def release_cuda_context(self) -> None:
+        native = object.__getattribute__(self, "_native")
+        if native is not None:
+            native.release_cuda_context()
 
     def scrub_and_verify(self, nbytes: int = 0) -> ScrubReport:
         native = object.__getattribute__(self, "_native")

@@ -121,6 +121,10 @@ class CCManager:
         # on which less than this fraction of device memory could be mapped fails the gate
         # (something else still holds HBM, so part of it was NOT scrubbed).
         self.scrub_min_coverage = float(env.get("CC_SCRUB_MIN_COVERAGE", "0.90"))
+        # A CUDA context must not outlive the gate: it pins HBM, blocks a vfio re-bind and would
+        # not survive the next transition's device reset.  (Benchmarks that share the process
+        # with other CUDA users switch this off.)
+        self.release_cuda_context = env.get("CC_RELEASE_CUDA_CONTEXT", "true").lower() == "true"
         self.concurrent_evict_wait = env.get("CC_CONCURRENT_EVICT_WAIT", "false").lower() == "true"
         self.journal_labels = env.get("CC_JOURNAL_COMPONENT_LABELS", "false").lower() == "true"
         self._device_source = device_source or _devices.find_gpus
@@ -367,6 +371,19 @@ class CCManager:
             logger.warning("CC_SCRUB_MODE=skip: releasing %d GPU(s) WITHOUT an HBM scrub", len(gpus))
             self.last_transition["scrub"] = "skipped"
             return
+        try:
+            self._run_scrub(gpus)
+        finally:
+            if self.release_cuda_context:
+                for gpu in gpus:
+                    release = getattr(gpu, "release_cuda_context", None)
+                    if release is not None:
+                        try:
+                            release()
+                        except Exception as exc:  # noqa: BLE001 - never mask the gate's own verdict
+                            logger.warning("Could not release the CUDA context on %s: %s", gpu.bdf, exc)
+
+    def _run_scrub(self, gpus: list) -> None:
         started = time.perf_counter()
         if all(isinstance(g, _devices.NvidiaDevice) for g in gpus) and self._workers(len(gpus)) == len(gpus):
             reports, _ = _devices.scrub_and_verify_many(gpus, self.scrub_bytes)

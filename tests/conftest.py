@@ -14,6 +14,10 @@ for p in (ROOT, ROOT / "tests", ROOT / "tests" / "fakes", ROOT / "oracle"):
 
 # The CPU suite drives the simulated register file; a GPU box picks cudasim itself.
 os.environ.setdefault("CC_READINESS_FILE", "/tmp/ccm-test-readiness/.cc-manager-ctr-ready")
+# The manager resets a GPU's CUDA primary context after the scrub gate (production default).
+# Inside ONE pytest process that context is shared with torch and with later tests, so the suite
+# keeps contexts alive; the release path is exercised in a subprocess (tests/test_context_release.py).
+os.environ.setdefault("CC_RELEASE_CUDA_CONTEXT", "false")
 
 
 def pytest_configure(config):
