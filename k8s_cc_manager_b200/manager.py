@@ -125,6 +125,12 @@ class CCManager:
         # not survive the next transition's device reset.  (Benchmarks that share the process
         # with other CUDA users switch this off.)
         self.release_cuda_context = env.get("CC_RELEASE_CUDA_CONTEXT", "true").lower() == "true"
+        # 'thread': the gate runs inside this process (libccm's concurrent launcher).
+        # 'process': it runs in a short-lived `scrub_worker` child, so no CUDA state survives in
+        # the daemon and a CUDA fault cannot take the control loop down.
+        self.scrub_isolation = env.get("CC_SCRUB_ISOLATION", "thread").lower()
+        if self.scrub_isolation not in ("thread", "process"):
+            raise ValueError(f"CC_SCRUB_ISOLATION must be 'thread' or 'process', not {self.scrub_isolation!r}")
         self.concurrent_evict_wait = env.get("CC_CONCURRENT_EVICT_WAIT", "false").lower() == "true"
         self.journal_labels = env.get("CC_JOURNAL_COMPONENT_LABELS", "false").lower() == "true"
         self._device_source = device_source or _devices.find_gpus
@@ -383,9 +389,29 @@ class CCManager:
                         except Exception as exc:  # noqa: BLE001 - never mask the gate's own verdict
                             logger.warning("Could not release the CUDA context on %s: %s", gpu.bdf, exc)
 
+    def _scrub_in_worker_process(self, gpus: list) -> list:
+        """CC_SCRUB_ISOLATION=process: one child runs the concurrent gate for all GPUs."""
+        import json as _json
+        import subprocess
+        cmd = [sys.executable, "-m", "k8s_cc_manager_b200.scrub_worker", "--bytes", str(self.scrub_bytes)]
+        for gpu in gpus:
+            cmd += ["--bdf", gpu.bdf]
+        env = dict(os.environ)
+        pkg_parent = str(Path(__file__).resolve().parents[1])
+        env["PYTHONPATH"] = pkg_parent + os.pathsep + env.get("PYTHONPATH", "")
+        proc = subprocess.run(cmd, capture_output=True, text=True, env=env,
+                              timeout=float(os.environ.get("CC_SCRUB_TIMEOUT_SECONDS", "600")))
+        lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+        if proc.returncode not in (0, 3) or not lines:
+            raise ScrubFailure(f"scrub worker failed (exit {proc.returncode}): {proc.stderr.strip()[-500:]}")
+        payload = _json.loads(lines[-1])
+        return [_devices.ScrubReport(**r) for r in payload["reports"]]
+
     def _run_scrub(self, gpus: list) -> None:
         started = time.perf_counter()
-        if all(isinstance(g, _devices.NvidiaDevice) for g in gpus) and self._workers(len(gpus)) == len(gpus):
+        if self.scrub_isolation == "process":
+            reports = self._scrub_in_worker_process(gpus)
+        elif all(isinstance(g, _devices.NvidiaDevice) for g in gpus) and self._workers(len(gpus)) == len(gpus):
             reports, _ = _devices.scrub_and_verify_many(gpus, self.scrub_bytes)
         else:
             def one(gpu):
