@@ -15,6 +15,8 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libccm.so"
+CLI_PATH = PKG_DIR / "ccm-scrub"
+CLI_SOURCE = CSRC / "ccm_scrub_cli.cpp"
 
 SOURCES = [CSRC / "ccm_scrub.cu", CSRC / "ccm_core.cpp"]
 HEADERS = [CSRC / "scrub_kernels.cuh", CSRC / "ccm_internal.h", REPO_ROOT / "include" / "ccm.h"]
@@ -36,10 +38,10 @@ def find_nvcc() -> str:
 
 
 def needs_build() -> bool:
-    if not LIB_PATH.exists():
+    if not LIB_PATH.exists() or not CLI_PATH.exists():
         return True
-    built = LIB_PATH.stat().st_mtime
-    return any(p.stat().st_mtime > built for p in SOURCES + HEADERS + [Path(__file__)])
+    built = min(LIB_PATH.stat().st_mtime, CLI_PATH.stat().st_mtime)
+    return any(p.stat().st_mtime > built for p in SOURCES + HEADERS + [CLI_SOURCE, Path(__file__)])
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -56,6 +58,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError(f"nvcc failed ({proc.returncode}) building {LIB_PATH}")
     if verbose:
         sys.stderr.write(proc.stderr)
+    # native CLI front end (ccm-scrub): plain host C++, finds libccm.so next to itself
+    gxx = shutil.which("g++") or "g++"
+    cli = subprocess.run([gxx, "-O2", "-std=c++17", "-Wall", "-I", str(REPO_ROOT / "include"), str(CLI_SOURCE),
+                          "-o", str(CLI_PATH), "-L", str(PKG_DIR), "-lccm", "-Wl,-rpath,$ORIGIN"],
+                         capture_output=True, text=True)
+    if cli.returncode != 0:
+        sys.stderr.write(cli.stdout + cli.stderr)
+        raise RuntimeError(f"g++ failed ({cli.returncode}) building {CLI_PATH}")
     return LIB_PATH
 
 

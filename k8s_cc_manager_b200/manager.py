@@ -393,7 +393,11 @@ class CCManager:
         """CC_SCRUB_ISOLATION=process: one child runs the concurrent gate for all GPUs."""
         import json as _json
         import subprocess
-        cmd = [sys.executable, "-m", "k8s_cc_manager_b200.scrub_worker", "--bytes", str(self.scrub_bytes)]
+        native_cli = Path(__file__).resolve().parent / "ccm-scrub"
+        if native_cli.exists() and os.environ.get("CC_SCRUB_WORKER", "native") == "native":
+            cmd = [str(native_cli), "--bytes", str(self.scrub_bytes)]   # no interpreter start-up in the child
+        else:
+            cmd = [sys.executable, "-m", "k8s_cc_manager_b200.scrub_worker", "--bytes", str(self.scrub_bytes)]
         for gpu in gpus:
             cmd += ["--bdf", gpu.bdf]
         env = dict(os.environ)
