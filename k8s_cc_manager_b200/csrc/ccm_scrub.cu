@@ -309,6 +309,17 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
     }
     case CCM_SCRUB_ST256: {
       RegionSplit s = split_region(p, n, 32, 128);
+      if (cfg == nullptr) {
+        // library default: compile-time shape (148 persistent CTAs x 512 threads, 8 x STG.256 per
+        // thread per 128 KiB grab) — scrub_st256_fast_kernel
+        constexpr int kThreads = 512, kPer = 8;
+        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)kThreads * kPer * 32);
+        CCM_CUDA(cudaMemsetAsync(e->d_counter + 8, 0, sizeof(unsigned long long), st));
+        scrub_st256_fast_kernel<kThreads, kPer, kPolDefault><<<e->sm_count, kThreads, 0, st>>>(s, nchunks, e->d_counter + 8);
+        err = cudaGetLastError();
+        g_launches++;
+        break;
+      }
       Sched sc;
       if (int rc = make_sched(e, sh, s.body_vecs * 32, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
       err = launch_scrub_st<32>(s, grid, sh, sc, st);
@@ -370,6 +381,17 @@ static int verify_range(ScrubEngine* e, const void* p, uint64_t n, int variant, 
     }
     case CCM_VERIFY_LD256: {
       RegionSplit s = split_region(p, n, 32, 128);
+      if (cfg == nullptr) {
+        // library default: 148 persistent CTAs x 1024 threads, 4 x LDG.256 in flight per thread
+        // per 128 KiB grab — verify_ld256_fast_kernel
+        constexpr int kThreads = 1024, kPer = 4;
+        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)kThreads * kPer * 32);
+        CCM_CUDA(cudaMemsetAsync(e->d_counter + 8, 0, sizeof(unsigned long long), st));
+        verify_ld256_fast_kernel<kThreads, kPer, kPolStreaming><<<e->sm_count, kThreads, 0, st>>>(
+            s, nchunks, e->d_counter + 8, e->d_counter);
+        err = cudaGetLastError();
+        break;
+      }
       Sched sc;
       if (int rc = make_sched(e, sh, s.body_vecs * 32, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
       err = launch_verify_ld<32>(s, grid, sh, e->d_counter, sc, st);

@@ -218,6 +218,46 @@ scrub_st_kernel(RegionSplit s, Sched sched) {
   }
 }
 
+// ----------------------------------------------------- default shapes, tight loops
+// The two kernels below are what AUTO launches.  Same algorithm as scrub_st_kernel /
+// verify_ld_kernel with a per-CTA dynamic schedule, but block size and vectors per thread
+// are compile-time constants, so one chunk = THREADS * PER_THREAD * 32 bytes is addressed
+// from ONE 64-bit base with immediate offsets: PER_THREAD STG.256 / LDG.256 per thread per
+// chunk and ~10 instructions of bookkeeping, instead of ~13 instructions per store in the
+// generic kernel (runtime stride => a 64-bit add pair per access).  Same GB/s — the kernels
+// are egress / DRAM bound — fewer issued instructions, less power.
+template <int THREADS, int PER_THREAD, int POL>
+__global__ void __launch_bounds__(THREADS)
+scrub_st256_fast_kernel(RegionSplit s, uint64_t nchunks, unsigned long long* grab) {
+  constexpr uint64_t kChunk = (uint64_t)THREADS * PER_THREAD * 32;
+  uint8_t* body = s.base + s.head;
+  __shared__ unsigned long long s_chunk[2];
+  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(grab, 1ull);
+  __syncthreads();
+  int buf = 0;
+  for (;;) {
+    const uint64_t c = s_chunk[buf];
+    if (c >= nchunks) break;
+    unsigned long long nxt = 0;
+    if (threadIdx.x == 0) nxt = atomicAdd(grab, 1ull);  // next grab in flight while we store
+    uint8_t* p = body + c * kChunk + threadIdx.x * 32u;
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; ++u) st_zero32<POL>(p + (uint32_t)u * THREADS * 32u);
+    if (threadIdx.x == 0) s_chunk[buf ^ 1] = nxt;
+    __syncthreads();
+    buf ^= 1;
+  }
+  // vectors after the last whole chunk (< kChunk bytes), then the ragged head / tail bytes
+  for (uint64_t i = nchunks * (kChunk / 32) + (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+       i < s.body_vecs; i += (uint64_t)gridDim.x * THREADS)
+    st_zero32<POL>(body + i * 32);
+  if (blockIdx.x == 0) {
+    for (uint64_t i = threadIdx.x; i < s.head; i += THREADS) s.base[i] = 0;
+    uint8_t* t = body + s.body_vecs * 32;
+    for (uint64_t i = threadIdx.x; i < s.tail; i += THREADS) t[i] = 0;
+  }
+}
+
 // ------------------------------------------------------ scrub (TMA bulk store)
 // One zeroed shared-memory tile per CTA is the source of EVERY bulk store: it
 // never changes, so there is no WAR hazard and no per-op wait — the issuing lane
@@ -414,6 +454,56 @@ verify_ld_kernel(RegionSplit s, unsigned long long* counter, Sched sched) {
     for (uint64_t i = threadIdx.x; i < s.head; i += blockDim.x) cnt += (s.base[i] != 0);
     const uint8_t* t = body + s.body_vecs * VB;
     for (uint64_t i = threadIdx.x; i < s.tail; i += blockDim.x) cnt += (t[i] != 0);
+  }
+  block_accumulate(cnt, counter);
+}
+
+template <int THREADS, int PER_THREAD, int POL>
+__global__ void __launch_bounds__(THREADS)
+verify_ld256_fast_kernel(RegionSplit s, uint64_t nchunks, unsigned long long* grab, unsigned long long* counter) {
+  constexpr uint64_t kChunk = (uint64_t)THREADS * PER_THREAD * 32;
+  const uint8_t* body = s.base + s.head;
+  uint64_t cnt = 0;
+  __shared__ unsigned long long s_chunk[2];
+  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(grab, 1ull);
+  __syncthreads();
+  int buf = 0;
+  for (;;) {
+    const uint64_t c = s_chunk[buf];
+    if (c >= nchunks) break;
+    unsigned long long nxt = 0;
+    if (threadIdx.x == 0) nxt = atomicAdd(grab, 1ull);
+    const uint8_t* p = body + c * kChunk + threadIdx.x * 32u;
+    Vec32 v[PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; ++u) v[u] = ld32<POL>(p + (uint32_t)u * THREADS * 32u);  // all loads first
+    uint32_t any = 0;
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) any |= v[u].w[k];
+    if (any != 0) {  // rare: exact per-byte count of this batch
+      uint32_t n = 0;
+#pragma unroll
+      for (int u = 0; u < PER_THREAD; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) n += nonzero_bytes_in_word(v[u].w[k]);
+      cnt += n;
+    }
+    if (threadIdx.x == 0) s_chunk[buf ^ 1] = nxt;
+    __syncthreads();
+    buf ^= 1;
+  }
+  for (uint64_t i = nchunks * (kChunk / 32) + (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+       i < s.body_vecs; i += (uint64_t)gridDim.x * THREADS) {
+    Vec32 v = ld32<POL>(body + i * 32);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cnt += nonzero_bytes_in_word(v.w[k]);
+  }
+  if (blockIdx.x == 0) {
+    for (uint64_t i = threadIdx.x; i < s.head; i += THREADS) cnt += (s.base[i] != 0);
+    const uint8_t* t = body + s.body_vecs * 32;
+    for (uint64_t i = threadIdx.x; i < s.tail; i += THREADS) cnt += (t[i] != 0);
   }
   block_accumulate(cnt, counter);
 }
