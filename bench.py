@@ -343,12 +343,12 @@ def run_ours(args):
         },
         "per_gpu": {"scrub_gbs": R / scrub_ms / 1e6, "verify_gbs": R / verify_ms / 1e6,
                     "scrub_ms": scrub_ms, "verify_ms": verify_ms, "step_gbs": 2.0 * R * args.steps / ms_local / 1e6},
-        "roofline": {"bound": "hbm", "kernel": "scrub_st_kernel (HBM write)", "achieved": R / scrub_ms / 1e6,
+        "roofline": {"bound": "hbm", "kernel": "scrub_st256_fast_kernel<512,8> (HBM write)", "achieved": R / scrub_ms / 1e6,
                      "peak": peak, "unit": "GB/s", "frac": R / scrub_ms / 1e6 / peak, "traffic": traffic_s,
                      "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write of one full-arena launch)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": R, "note": "of measured" if "MEASURED" in peak_src else "of fallback"},
-        "roofline_verify": {"bound": "hbm", "kernel": "verify_ld_kernel (HBM read)", "achieved": R / verify_ms / 1e6,
+        "roofline_verify": {"bound": "hbm", "kernel": "verify_ld256_fast_kernel<1024,4> (HBM read)", "achieved": R / verify_ms / 1e6,
                             "peak": peak, "unit": "GB/s", "frac": R / verify_ms / 1e6 / peak, "traffic": traffic_v,
                             "algorithmic_bytes_per_launch": R},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
