@@ -350,3 +350,25 @@ def test_multi_gpu_concurrent_gate(lib, monkeypatch):
     assert mgr.set_cc_mode("on") is True
     assert len(mgr.last_transition["scrub"]) == len(gpus)
     assert c.labels("n")["nvidia.com/cc.mode.state"] == "on"
+
+
+def test_same_device_calls_from_many_threads_serialise(lib):
+    """Per-device mutex: concurrent product calls on ONE GPU must all succeed and stay exact."""
+    import threading
+    from k8s_cc_manager_b200 import devices as D
+    ok(lib.ccm_init(N.BACKEND_CUDASIM))
+    gpu = [d for d in D.find_gpus()[0] if d.is_gpu()][0]
+    results, errors = [], []
+
+    def work(i):
+        try:
+            results.append(gpu.scrub_and_verify((1 << 30) + i * (2 << 20)))
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    assert len(results) == 6 and all(r.clean for r in results)
+    assert sorted(r.bytes_scrubbed for r in results) == [(1 << 30) + i * (2 << 20) for i in range(6)]
