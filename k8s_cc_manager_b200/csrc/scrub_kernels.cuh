@@ -11,10 +11,18 @@
 // Region decomposition (any pointer, any length):
 //   [ head bytes | body: whole VB-byte vectors, VB-aligned | tail bytes ]
 // head/tail are < 128+VB bytes and are handled with byte accesses by CTA 0; the
-// body is tiled  tile = threads * UNROLL vectors  and grid-strided by persistent
-// CTAs (grid = ctas_per_sm * #SMs), so at any instant the whole chip writes one
-// moving window of grid*tile bytes (a few tens of MB: inside TLB reach, and every
-// warp instruction covers whole 128-byte lines -> only full-sector writes).
+// body is cut into tiles (tile = threads * UNROLL vectors; every warp instruction
+// covers whole 128-byte lines -> only full-sector writes) that are handed to
+// PERSISTENT CTAs (grid = ctas_per_sm * #SMs) either statically (grid-stride) or —
+// the default — dynamically: a CTA grabs the next chunk of tiles off an atomic
+// counter, so SMs that drain faster take more work (see "work distribution").
+//
+// Kernels in this file:
+//   scrub_st256_fast_kernel / verify_ld256_fast_kernel   what AUTO launches (compile-time shape)
+//   scrub_st_kernel / verify_ld_kernel                   any shape / width / policy / schedule
+//   scrub_tma_kernel                                     cp.async.bulk stores from one zero tile
+//   verify_tma_kernel                                    cp.async.bulk loads into an mbarrier ring
+//   fill_pattern_kernel                                  seeded test pattern (tests only)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
