@@ -41,7 +41,8 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built -fvisibility=hidden */
 #endif
 
-#define CCM_ABI_VERSION 1
+#define CCM_ABI_VERSION 2 /* v2: deferred release, coverage fields; ccm_transition_many and the
+                             TMA verify variant removed (one phase engine, one verify family) */
 
 /* ---- status codes ------------------------------------------------------- */
 typedef enum ccm_status {
@@ -126,17 +127,6 @@ int ccm_reset(int dev);
 /* dev.wait_for_boot()      reference main.py:347,372,494,523; timeout_ms<=0 = default */
 int ccm_wait_for_boot(int dev, int timeout_ms);
 
-/* Batched, CONCURRENT form of reference main.py:502-529 for `n` devices:
- * phase A stage all (query; set if different) -> barrier -> phase B reset all that
- * changed -> barrier -> phase C wait_for_boot + verify mode on each.  One host
- * thread per device, joined between phases so the reference's "stage all, then
- * reset all, then verify all" ordering (main.py:455-459) is preserved.
- * status[i] receives the per-device ccm_status; changed[i] is 1 if device i was
- * staged+reset.  is_ppcie selects the PPCIe register pair (main.py:349-378).
- * Returns CCM_OK iff every device succeeded and reads back `mode`. */
-int ccm_transition_many(int n, const int* devs, int mode, int is_ppcie,
-                        int boot_timeout_ms, int* status, int* changed);
-
 /* ---- HBM scrub-and-verify (NEW stage) ------------------ */
 typedef enum ccm_scrub_variant {
   CCM_SCRUB_AUTO = 0,
@@ -149,8 +139,7 @@ typedef enum ccm_scrub_variant {
 typedef enum ccm_verify_variant {
   CCM_VERIFY_AUTO = 0,
   CCM_VERIFY_LD128 = 1,  /* ld.global.nc.v4.b32                                 */
-  CCM_VERIFY_LD256 = 2,  /* ld.global.nc.v8.b32 (256-bit)                       */
-  CCM_VERIFY_TMA = 3     /* cp.async.bulk.shared.global ring + smem reduce      */
+  CCM_VERIFY_LD256 = 2   /* ld.global.nc.v8.b32 (256-bit)                       */
 } ccm_verify_variant;
 
 /* Launch shape override; zeros mean "library default for this variant". */
@@ -172,24 +161,48 @@ typedef struct ccm_scrub_result {
   uint64_t bytes_scrubbed;     /* bytes actually zeroed and read back           */
   uint64_t device_total_bytes; /* cudaMemGetInfo total — coverage denominator   */
   uint64_t nonzero_bytes;      /* EXACT count of bytes != 0 found by verify     */
-  double ms_acquire;           /* obtaining the arena (host wall-clock)         */
-  double ms_scrub;             /* CUDA-event time of the scrub kernel(s)        */
-  double ms_verify;            /* CUDA-event time of the verify kernel(s)       */
-  double ms_release;           /* freeing the arena (host wall-clock)           */
-  double ms_total;             /* host wall-clock of the whole call             */
-  int32_t segments;            /* arena segments (1 unless HBM is fragmented)   */
+  double ms_acquire;           /* host time inside create/map/set-access; it
+                                  overlaps the GPU work (chunk i is scrubbed
+                                  while chunk i+1 is being mapped)              */
+  double ms_scrub;             /* sum of the scrub kernels' CUDA-event times    */
+  double ms_verify;            /* sum of the verify kernels' CUDA-event times   */
+  double ms_release;           /* unmap + release when done inside the call; 0
+                                  when release_deferred (ask
+                                  ccm_scrub_release_wait for the real figure)   */
+  double ms_total;             /* host wall-clock of the call = time to verdict */
+  int32_t segments;            /* physical chunks mapped                        */
   int32_t scrub_variant;       /* variant that actually ran                     */
   int32_t verify_variant;
   int32_t sm_count;
   int32_t status;              /* ccm_status of this device (batched calls)     */
-  int32_t reserved;
+  int32_t release_deferred;    /* 1: the HBM is being handed back by the
+                                  engine's background reaper (see below)        */
+  /* ---- ABI v2 ---- */
+  uint64_t device_free_before; /* cudaMemGetInfo free when the call started     */
+  uint64_t bytes_unreached;    /* free HBM that could NOT be mapped and was
+                                  therefore not scrubbed (0 on a clean device)  */
+  double ms_release_wait;      /* time this call waited for the PREVIOUS call's
+                                  deferred release before it could start        */
+  double ms_gpu_span;          /* first scrub launch .. last verify done on the
+                                  stream (includes waiting for mappings)        */
 } ccm_scrub_result;
 
 /* The product call.  Obtains `bytes` of HBM on device `dev` (0 = everything the
- * context can map), zero-fills it, reads it back, counts non-zero bytes, frees
- * it.  Returns CCM_ERR_DIRTY if nonzero_bytes != 0, CCM_ERR_NO_CUDA when the
- * device has no CUDA ordinal.  Never falls back to a host path. */
+ * context can map, down to the last 2 MiB granule), zero-fills it, reads it back
+ * and counts non-zero bytes.  The verdict is returned as soon as the count is on the
+ * host; handing the HBM back to the driver (cuMemUnmap / cuMemRelease — the most
+ * expensive part of the call, 0.33 ms/GiB, serialised node-wide by the driver)
+ * runs on a per-device background thread.  That "reaper" is joined by the next
+ * scrub / arena call on the device, by ccm_scrub_release_wait() and by
+ * ccm_device_release(); CCM_ASYNC_RELEASE=0 keeps the release inside the call.
+ * Returns CCM_ERR_DIRTY if nonzero_bytes != 0, CCM_ERR_NO_CUDA when the device has
+ * no CUDA ordinal.  Never falls back to a host path. */
 int ccm_scrub_verify(int dev, uint64_t bytes, ccm_scrub_result* out);
+
+/* Blocks until the HBM of the last ccm_scrub_verify() on `dev` is back with the
+ * driver.  *ms_release (optional) = duration of that background release,
+ * *ms_waited (optional) = how long THIS call blocked.  CCM_OK when nothing is pending. */
+int ccm_scrub_release_wait(int dev, double* ms_release, double* ms_waited);
 
 /* Concurrent multi-context launcher: one host thread + primary context + stream
  * per device, no peer access, no collective.  out[i].status is per device;
@@ -248,9 +261,12 @@ int ccm_host_roundtrip(int cuda_ordinal, void* host_buf, uint64_t bytes, uint64_
  * counters — and resets that device's primary context (cudaDeviceReset).  A daemon must not sit
  * on a CUDA context between transitions: the context pins ~0.5 GB of HBM, keeps the GPU "in use"
  * (it cannot be unbound for vfio) and does not survive the device reset of the next transition
- * (reference main.py:519).  The next scrub call re-creates what it needs.  The sysfs backend
+ * (reference main.py:519).  Joins the background release of the last scrub first.  The next scrub
+ * call re-creates what it needs.  The sysfs backend
  * calls this implicitly before it resets a device.  No-op (CCM_OK) when nothing is held. */
 int ccm_device_release(int dev);
+/* Concurrent form for `n` devices (one host thread each); *wall_ms = host wall-clock. */
+int ccm_device_release_many(int n, const int* devs, double* wall_ms);
 
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t ccm_kernel_launches(void);
@@ -260,7 +276,10 @@ uint64_t ccm_kernel_launches(void);
 int ccm_sim_topology(int n_gpus, int n_switches);
 /* key: "cc_mode" "ppcie_mode" "cc_supported" "ppcie_supported" "reset_ms"
  *      "boot_ms" "fail_op" (bitmask of ccm_sim_op) "stuck" (reset ignores staged)
- *      "cuda_ordinal".   dev = -1 applies to every device. */
+ *      "cuda_ordinal" "scrub_inject" (fault drill: ccm_scrub_verify poisons that many bytes
+ *      between the scrub and the read-back — first, unaligned, middle and last byte of each
+ *      chunk — so the call must come back CCM_ERR_DIRTY with nonzero_bytes == min(value, 4 x
+ *      chunks)).   dev = -1 applies to every device. */
 int ccm_sim_set(int dev, const char* key, int64_t value);
 int ccm_sim_get(int dev, const char* key, int64_t* value);
 typedef enum ccm_sim_op {

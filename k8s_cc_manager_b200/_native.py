@@ -40,9 +40,11 @@ BACKEND_SIM, BACKEND_CUDASIM, BACKEND_SYSFS = 0, 1, 2
 BACKENDS = {"sim": BACKEND_SIM, "cudasim": BACKEND_CUDASIM, "sysfs": BACKEND_SYSFS}
 
 SCRUB_AUTO, SCRUB_ST128, SCRUB_ST256, SCRUB_TMA, SCRUB_MEMSET = 0, 1, 2, 3, 4
-VERIFY_AUTO, VERIFY_LD128, VERIFY_LD256, VERIFY_TMA = 0, 1, 2, 3
+VERIFY_AUTO, VERIFY_LD128, VERIFY_LD256 = 0, 1, 2
 SCRUB_VARIANTS = {"auto": 0, "st128": 1, "st256": 2, "tma": 3, "memset": 4}
-VERIFY_VARIANTS = {"auto": 0, "ld128": 1, "ld256": 2, "tma": 3}
+VERIFY_VARIANTS = {"auto": 0, "ld128": 1, "ld256": 2}
+
+ABI_VERSION = 2  # include/ccm.h: CCM_ABI_VERSION
 
 OP_QUERY_CC, OP_SET_CC, OP_QUERY_PPCIE, OP_SET_PPCIE, OP_RESET, OP_WAIT_BOOT, OP_SCRUB = 1, 2, 4, 8, 16, 32, 64
 
@@ -88,11 +90,15 @@ class ScrubResult(C.Structure):
         ("verify_variant", C.c_int32),
         ("sm_count", C.c_int32),
         ("status", C.c_int32),
-        ("reserved", C.c_int32),
+        ("release_deferred", C.c_int32),
+        ("device_free_before", C.c_uint64),
+        ("bytes_unreached", C.c_uint64),
+        ("ms_release_wait", C.c_double),
+        ("ms_gpu_span", C.c_double),
     ]
 
     def as_dict(self) -> dict:
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+        return {name: getattr(self, name) for name, _ in self._fields_}
 
 
 class ArenaInfo(C.Structure):
@@ -121,9 +127,9 @@ _SIGNATURES = {
     "ccm_set_ppcie_mode": (C.c_int, [C.c_int, C.c_int]),
     "ccm_reset": (C.c_int, [C.c_int]),
     "ccm_wait_for_boot": (C.c_int, [C.c_int, C.c_int]),
-    "ccm_transition_many": (C.c_int, [C.c_int, _P(C.c_int), C.c_int, C.c_int, C.c_int, _P(C.c_int), _P(C.c_int)]),
     "ccm_scrub_verify": (C.c_int, [C.c_int, C.c_uint64, _P(ScrubResult)]),
     "ccm_scrub_verify_many": (C.c_int, [C.c_int, _P(C.c_int), C.c_uint64, _P(ScrubResult), _P(C.c_double)]),
+    "ccm_scrub_release_wait": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_double)]),
     "ccm_arena_acquire": (C.c_int, [C.c_int, C.c_uint64, _P(ArenaInfo)]),
     "ccm_arena_release": (C.c_int, [C.c_int]),
     "ccm_arena_scrub": (C.c_int, [C.c_int, C.c_int, _P(LaunchCfg), C.c_void_p, _P(C.c_float)]),
@@ -139,6 +145,7 @@ _SIGNATURES = {
     "ccm_region_verify": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_int, _P(LaunchCfg), C.c_void_p, _P(C.c_uint64), _P(C.c_float)]),
     "ccm_host_roundtrip": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _P(C.c_uint64), _P(C.c_uint64)]),
     "ccm_device_release": (C.c_int, [C.c_int]),
+    "ccm_device_release_many": (C.c_int, [C.c_int, _P(C.c_int), _P(C.c_double)]),
     "ccm_kernel_launches": (C.c_uint64, []),
     "ccm_sim_topology": (C.c_int, [C.c_int, C.c_int]),
     "ccm_sim_set": (C.c_int, [C.c_int, C.c_char_p, C.c_int64]),
@@ -178,8 +185,8 @@ def lib() -> C.CDLL:
                 raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from exc
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.ccm_abi_version() != 1:
-            raise NativeLibraryError(f"{LIB_PATH}: ABI version {handle.ccm_abi_version()} != 1")
+        if handle.ccm_abi_version() != ABI_VERSION:
+            raise NativeLibraryError(f"{LIB_PATH}: ABI version {handle.ccm_abi_version()} != {ABI_VERSION}")
         _lib = handle
     return _lib
 

@@ -56,6 +56,7 @@ struct Device {
   int reset_ms = 0, boot_ms = 0;
   uint32_t fail_mask = 0;  // ccm_sim_op bits that return CCM_ERR_FAULT
   bool stuck = false;      // reset does not apply staged values
+  uint64_t scrub_inject = 0;  // fault drill: bytes poisoned between scrub and read-back
   std::string sysfs_path;  // sysfs backend
 };
 
@@ -266,9 +267,10 @@ int cuda_ordinal_of(int dev) {
   return ord;
 }
 
-int sim_scrub_hook(int dev) {
+int sim_scrub_hook(int dev, uint64_t* inject) {
   return with_dev(dev, [&](Device& d) {
     trace(d, "scrub", nullptr);
+    if (inject) *inject = g_backend == CCM_BACKEND_SYSFS ? 0 : d.scrub_inject;
     if (d.fail_mask & CCM_OP_SCRUB) { set_error("injected fault: scrub on %s", d.info.bdf); return (int)CCM_ERR_FAULT; }
     return (int)CCM_OK;
   });
@@ -465,64 +467,6 @@ int ccm_set_ppcie_mode(int dev, int mode) { return with_dev(dev, [&](Device& d) 
 int ccm_reset(int dev) { return with_dev(dev, [&](Device& d) { return op_reset(d); }); }
 int ccm_wait_for_boot(int dev, int timeout_ms) { return with_dev(dev, [&](Device& d) { return op_wait_boot(d, timeout_ms); }); }
 
-// Concurrent form of reference main.py:502-529 (CC) / main.py:349-378 (PPCIe).
-int ccm_transition_many(int n, const int* devs, int mode, int is_ppcie, int boot_timeout_ms,
-                        int* status, int* changed) {
-  if (n < 0 || (n > 0 && !devs)) return CCM_ERR_INVALID;
-  std::vector<int> st(n, CCM_OK), ch(n, 0);
-  std::vector<std::string> errs(n);
-  auto fan_out = [&](auto&& fn) {
-    std::vector<std::thread> th;
-    th.reserve(n);
-    for (int i = 0; i < n; ++i)
-      th.emplace_back([&, i] {
-        if (st[i] != CCM_OK) return;
-        st[i] = fn(i);
-        if (st[i] != CCM_OK) errs[i] = last_error();
-      });
-    for (auto& t : th) t.join();  // barrier between phases
-  };
-  // phase A: stage (reference main.py:504-512)
-  fan_out([&](int i) {
-    int cur = -1;
-    int rc = is_ppcie ? ccm_query_ppcie_mode(devs[i], &cur) : ccm_query_cc_mode(devs[i], &cur);
-    if (rc) return rc;
-    if (cur == mode) return (int)CCM_OK;
-    rc = is_ppcie ? ccm_set_ppcie_mode(devs[i], mode) : ccm_set_cc_mode(devs[i], mode);
-    if (rc == CCM_OK) ch[i] = 1;
-    return rc;
-  });
-  // The reference aborts the whole transition on the first staging error
-  // (exception leaves the try block at main.py:502-529): no device is reset.
-  bool abort = false;
-  for (int i = 0; i < n; ++i) abort |= (st[i] != CCM_OK);
-  if (!abort) {
-    // phase B: reset every staged device (reference main.py:515-519)
-    fan_out([&](int i) { return ch[i] ? ccm_reset(devs[i]) : (int)CCM_OK; });
-    // phase C: wait for boot + read back (reference main.py:522-529)
-    fan_out([&](int i) {
-      if (!ch[i]) return (int)CCM_OK;
-      int rc = ccm_wait_for_boot(devs[i], boot_timeout_ms);
-      if (rc) return rc;
-      int cur = -1;
-      rc = is_ppcie ? ccm_query_ppcie_mode(devs[i], &cur) : ccm_query_cc_mode(devs[i], &cur);
-      if (rc) return rc;
-      if (cur != mode) {
-        set_error("mode verification failed on device %d: expected %d, got %d", devs[i], mode, cur);
-        return (int)CCM_ERR_IO;
-      }
-      return (int)CCM_OK;
-    });
-  }
-  int rc = CCM_OK;
-  for (int i = 0; i < n; ++i) {
-    if (status) status[i] = st[i];
-    if (changed) changed[i] = ch[i];
-    if (st[i] != CCM_OK && rc == CCM_OK) { rc = st[i]; set_error("%s", errs[i].c_str()); }
-  }
-  return rc;
-}
-
 // ------------------------------------------------------------------ scrub ABI
 static ScrubEngine* engine_of_dev(int dev, int* rc) {
   int ord = cuda_ordinal_of(dev);
@@ -540,10 +484,18 @@ static ScrubEngine* engine_of_ordinal(int ordinal, int* rc) {
 
 int ccm_scrub_verify(int dev, uint64_t bytes, ccm_scrub_result* out) {
   if (out) { memset(out, 0, sizeof *out); out->bytes_requested = bytes; }
-  int rc = sim_scrub_hook(dev);
+  uint64_t inject = 0;
+  int rc = sim_scrub_hook(dev, &inject);
   ScrubEngine* e = rc ? nullptr : engine_of_dev(dev, &rc);
   if (!e) { if (out) out->status = rc; return rc; }
-  return engine_scrub_verify(e, bytes, out);
+  return engine_scrub_verify(e, bytes, inject, out);
+}
+
+int ccm_scrub_release_wait(int dev, double* ms_release, double* ms_waited) {
+  if (ms_release) *ms_release = 0;
+  if (ms_waited) *ms_waited = 0;
+  int rc; ScrubEngine* e = engine_of_dev(dev, &rc);
+  return e ? engine_release_wait(e, ms_release, ms_waited) : rc;
 }
 
 int ccm_scrub_verify_many(int n, const int* devs, uint64_t bytes, ccm_scrub_result* out, double* wall_ms) {
@@ -634,6 +586,25 @@ int ccm_device_release(int dev) {
   return ord >= 0 ? engine_teardown(ord) : (int)CCM_OK;
 }
 
+int ccm_device_release_many(int n, const int* devs, double* wall_ms) {
+  if (n < 0 || (n > 0 && !devs)) return CCM_ERR_INVALID;
+  const auto t0 = Clock::now();
+  std::vector<int> rcs(n, CCM_OK);
+  std::vector<std::string> errs(n);
+  std::vector<std::thread> th;
+  th.reserve(n);
+  for (int i = 0; i < n; ++i)
+    th.emplace_back([&, i] {
+      rcs[i] = ccm_device_release(devs[i]);
+      if (rcs[i]) errs[i] = last_error();
+    });
+  for (auto& t : th) t.join();
+  if (wall_ms) *wall_ms = std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+  for (int i = 0; i < n; ++i)
+    if (rcs[i] != CCM_OK) { set_error("%s", errs[i].c_str()); return rcs[i]; }
+  return CCM_OK;
+}
+
 uint64_t ccm_kernel_launches(void) { return kernel_launches(); }
 
 // ------------------------------------------------------------------ sim knobs
@@ -657,6 +628,7 @@ static int sim_apply(Device& d, const std::string& k, int64_t v) {
   else if (k == "stuck") d.stuck = v != 0;
   else if (k == "cuda_ordinal") d.info.cuda_ordinal = (int)v;
   else if (k == "booted") d.booted = v != 0;
+  else if (k == "scrub_inject") d.scrub_inject = v < 0 ? 0 : (uint64_t)v;
   else { set_error("unknown sim key '%s'", k.c_str()); return CCM_ERR_INVALID; }
   return CCM_OK;
 }
@@ -692,6 +664,7 @@ int ccm_sim_get(int dev, const char* key, int64_t* value) {
     else if (k == "fail_op") *value = d.fail_mask;
     else if (k == "stuck") *value = d.stuck;
     else if (k == "cuda_ordinal") *value = d.info.cuda_ordinal;
+    else if (k == "scrub_inject") *value = (int64_t)d.scrub_inject;
     else { set_error("unknown sim key '%s'", k.c_str()); return (int)CCM_ERR_INVALID; }
     return (int)CCM_OK;
   });

@@ -34,7 +34,11 @@ int engine_arena_step_times(ScrubEngine*, int cap, float* scrub_ms, float* verif
 int engine_arena_fill(ScrubEngine*, int byte_value, void* stream);
 int engine_arena_fill_random(ScrubEngine*, uint64_t seed, void* stream);
 int engine_arena_rw(ScrubEngine*, uint64_t offset, void* host, uint64_t bytes, bool write);
-int engine_scrub_verify(ScrubEngine*, uint64_t bytes, ccm_scrub_result* out);
+// inject: fault drill (sim key "scrub_inject") — that many bytes are poisoned AFTER the scrub and
+// BEFORE the read-back (first / unaligned / middle / last byte of each chunk), so the verdict must be DIRTY.
+int engine_scrub_verify(ScrubEngine*, uint64_t bytes, uint64_t inject, ccm_scrub_result* out);
+// Joins the background release of the last product call (no-op when none is pending).
+int engine_release_wait(ScrubEngine*, double* ms_release, double* ms_waited);
 int engine_region_scrub(ScrubEngine*, void* dptr, uint64_t bytes, int variant,
                         const ccm_launch_cfg*, void* stream, float* ms);
 int engine_region_verify(ScrubEngine*, const void* dptr, uint64_t bytes, int variant,
@@ -48,7 +52,8 @@ int engine_teardown(int ordinal);
 // ---- implemented in ccm_core.cpp -------------------------------------------
 // Maps a device-table index to its CUDA ordinal (or a negative ccm_status).
 int cuda_ordinal_of(int dev);
-// sim fault hook for the scrub op (returns CCM_OK or CCM_ERR_FAULT) + trace line.
-int sim_scrub_hook(int dev);
+// sim fault hook for the scrub op (returns CCM_OK or CCM_ERR_FAULT) + trace line; *inject = the
+// device's "scrub_inject" drill value.
+int sim_scrub_hook(int dev, uint64_t* inject);
 
 }  // namespace ccm

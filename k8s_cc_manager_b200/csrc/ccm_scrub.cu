@@ -12,6 +12,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include <cuda.h>  // driver-API TYPES only: entry points are resolved at run time (no -lcuda)
@@ -63,6 +64,22 @@ int cuda_describe(int ordinal, char* bdf, size_t bdf_cap, char* name, size_t nam
 struct Segment { uint8_t* ptr; uint64_t bytes; };
 
 static constexpr int kMaxSteps = 64;
+static constexpr int kMaxPipeChunks = 32;
+
+// Word indices inside the engine's device control block (each on its own 64-byte line):
+//   [0] non-zero byte count of the current verify        [8] grab counter of the GENERIC kernels
+//   [16]/[24] grab + done of scrub_st256_fast_kernel      [32]/[40] grab + done of verify_ld256_fast_kernel
+// The fast kernels hand their pair back zeroed (GrabCtl), so they never share words with the
+// generic kernels, whose counter is memset by the host before every launch.
+static constexpr int kCtlWords = 64;
+static constexpr int kGenericGrab = 8, kScrubGrab = 16, kScrubDone = 24, kVerifyGrab = 32, kVerifyDone = 40;
+
+// One contiguous virtual range backed by VMM chunks (cuMemCreate / cuMemMap).
+struct VmmMapping {
+  CUdeviceptr base = 0;
+  uint64_t va_bytes = 0, mapped = 0;
+  std::vector<CUmemGenericAllocationHandle> handles;
+};
 
 struct ScrubEngine {
   int ordinal = -1;
@@ -73,35 +90,66 @@ struct ScrubEngine {
   cudaStream_t stream = nullptr;   // the engine's own non-blocking stream
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t step_ev[kMaxSteps][3] = {};
+  cudaEvent_t pipe_ev[kMaxPipeChunks][3] = {};
   int step_count = 0;
   unsigned long long* d_counter = nullptr;
   unsigned long long* h_counter = nullptr;  // pinned
   std::vector<Segment> segs;
   uint64_t arena_bytes = 0;
   size_t total_bytes = 0;
+  // deferred give-back of the last gate's HBM: runs off the caller's critical path and is
+  // joined by whoever needs the memory (or the context) next
+  std::thread reaper;
+  double reaper_ms = 0;        // duration of the last background release
+  bool reaper_failed = false;
 
-  int init() {
-    if (ready) return CCM_OK;
-    CCM_CUDA(cudaSetDevice(ordinal));
-    CCM_CUDA(cudaFree(0));  // force primary-context creation here, not inside a timed call
-    int v = 0;
-    CCM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ordinal));
-    sm_count = v;
-    CCM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ordinal));
-    smem_optin = (size_t)v;
-    CCM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    for (auto& e : ev) CCM_CUDA(cudaEventCreate(&e));
-    for (auto& s : step_ev) for (auto& e : s) CCM_CUDA(cudaEventCreate(&e));
-    CCM_CUDA(cudaMalloc(&d_counter, 256));
-    CCM_CUDA(cudaMemset(d_counter, 0, 256));
-    CCM_CUDA(cudaHostAlloc(&h_counter, 64, cudaHostAllocDefault));
-    size_t fr = 0;
-    CCM_CUDA(cudaMemGetInfo(&fr, &total_bytes));
-    ready = true;
-    return CCM_OK;
-  }
+  ~ScrubEngine() { if (reaper.joinable()) reaper.join(); }
+
+  int init();
   cudaStream_t pick(void* s) const { return s ? (cudaStream_t)s : stream; }
+  GrabCtl scrub_ctl() const { return GrabCtl{d_counter + kScrubGrab, d_counter + kScrubDone}; }
+  GrabCtl verify_ctl() const { return GrabCtl{d_counter + kVerifyGrab, d_counter + kVerifyDone}; }
+  // Waits for the background release of the previous gate (no-op when none is pending).
+  double join_reaper() {
+    if (!reaper.joinable()) return 0.0;
+    const double t0 = now_ms();
+    reaper.join();
+    return now_ms() - t0;
+  }
 };
+
+// default launch shapes of the two AUTO kernels
+static constexpr int kFastScrubThreads = 512, kFastScrubPer = 8;
+static constexpr int kFastVerifyThreads = 1024, kFastVerifyPer = 4;
+#define CCM_FAST_SCRUB scrub_st256_fast_kernel<kFastScrubThreads, kFastScrubPer, kPolDefault>
+#define CCM_FAST_VERIFY verify_ld256_fast_kernel<kFastVerifyThreads, kFastVerifyPer, kPolStreaming>
+
+int ScrubEngine::init() {
+  if (ready) return CCM_OK;
+  CCM_CUDA(cudaSetDevice(ordinal));
+  CCM_CUDA(cudaFree(0));  // force primary-context creation here, not inside a timed call
+  int v = 0;
+  CCM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ordinal));
+  sm_count = v;
+  CCM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, ordinal));
+  smem_optin = (size_t)v;
+  CCM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (auto& e : ev) CCM_CUDA(cudaEventCreate(&e));
+  for (auto& s : step_ev) for (auto& e : s) CCM_CUDA(cudaEventCreate(&e));
+  for (auto& s : pipe_ev) for (auto& e : s) CCM_CUDA(cudaEventCreate(&e));
+  CCM_CUDA(cudaMalloc(&d_counter, kCtlWords * sizeof(unsigned long long)));
+  CCM_CUDA(cudaMemset(d_counter, 0, kCtlWords * sizeof(unsigned long long)));
+  CCM_CUDA(cudaHostAlloc(&h_counter, 64, cudaHostAllocDefault));
+  // The product call maps HBM down to the last granule; CUDA loads kernel code lazily at the
+  // first launch and that needs device memory — make the two default kernels resident now.
+  cudaFuncAttributes fa;
+  CCM_CUDA(cudaFuncGetAttributes(&fa, CCM_FAST_SCRUB));
+  CCM_CUDA(cudaFuncGetAttributes(&fa, CCM_FAST_VERIFY));
+  size_t fr = 0;
+  CCM_CUDA(cudaMemGetInfo(&fr, &total_bytes));
+  ready = true;
+  return CCM_OK;
+}
 
 static std::mutex g_engines_mu;
 static std::vector<std::unique_ptr<ScrubEngine>> g_engines;
@@ -126,6 +174,15 @@ ScrubEngine* engine_for(int ordinal) {
   return e;
 }
 
+// Every engine_* entry point calls this right after taking e->mu: a concurrent
+// ccm_device_release / sysfs reset may have torn the engine down between engine_for() and the
+// lock, in which case it is rebuilt here instead of running on dead handles.
+#define CCM_ENSURE_READY(e)                        \
+  do {                                             \
+    int rc__ = (e)->init();                        \
+    if (rc__ != CCM_OK) return rc__;               \
+  } while (0)
+
 int engine_teardown(int ordinal) {
   ScrubEngine* e = nullptr;
   {
@@ -134,6 +191,7 @@ int engine_teardown(int ordinal) {
     e = g_engines[ordinal].get();
   }
   std::lock_guard<std::mutex> g(e->mu);
+  e->join_reaper();  // the last gate's HBM must be back with the driver before the context goes
   if (!e->ready) return CCM_OK;
   CCM_CUDA(cudaSetDevice(ordinal));
   cudaStreamSynchronize(e->stream);
@@ -142,6 +200,7 @@ int engine_teardown(int ordinal) {
   e->arena_bytes = 0;
   for (auto& ev : e->ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
   for (auto& st : e->step_ev) for (auto& ev : st) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+  for (auto& st : e->pipe_ev) for (auto& ev : st) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
   e->step_count = 0;
   if (e->d_counter) cudaFree(e->d_counter);
   if (e->h_counter) cudaFreeHost(e->h_counter);
@@ -174,9 +233,8 @@ static Shape scrub_shape(int variant, const ccm_launch_cfg* c) {
   return s;
 }
 static Shape verify_shape(int variant, const ccm_launch_cfg* c) {
-  Shape s;
-  if (variant == CCM_VERIFY_TMA) s = Shape{2, 288, 0, kPolDefault, 16384, 1};
-  else s = Shape{1, 1024, 4, kPolStreaming, 131072, 2};
+  (void)variant;
+  Shape s = Shape{1, 1024, 4, kPolStreaming, 131072, 2};
   if (c) {
     if (c->ctas_per_sm > 0) s.ctas_per_sm = c->ctas_per_sm;
     if (c->threads_per_cta > 0) s.threads = c->threads_per_cta;
@@ -191,7 +249,7 @@ static Shape verify_shape(int variant, const ccm_launch_cfg* c) {
 // AUTO = the fastest variant measured on B200 (profiles/README.md).  ST256 and TMA tie on
 // throughput (7 618 vs 7 607 GB/s); TMA draws ~5 % less board power (601 vs 631 W,
 // profiles/r1_power_probe.json), so a deployment that prefers joules can pin it with
-// CCM_SCRUB_VARIANT=tma (st128 | st256 | tma | memset; CCM_VERIFY_VARIANT=ld128 | ld256 | tma).
+// CCM_SCRUB_VARIANT=tma (st128 | st256 | tma | memset; CCM_VERIFY_VARIANT=ld128 | ld256).
 static int env_variant(const char* name, const char* const* names, int n, int dflt) {
   const char* v = getenv(name);
   if (!v || !*v) return dflt;
@@ -204,8 +262,8 @@ static int resolve_scrub_variant(int v) {
   return v == CCM_SCRUB_AUTO ? env_variant("CCM_SCRUB_VARIANT", names, 4, CCM_SCRUB_ST256) : v;
 }
 static int resolve_verify_variant(int v) {
-  static const char* const names[] = {"ld128", "ld256", "tma"};
-  return v == CCM_VERIFY_AUTO ? env_variant("CCM_VERIFY_VARIANT", names, 3, CCM_VERIFY_LD256) : v;
+  static const char* const names[] = {"ld128", "ld256"};
+  return v == CCM_VERIFY_AUTO ? env_variant("CCM_VERIFY_VARIANT", names, 2, CCM_VERIFY_LD256) : v;
 }
 
 template <int VB, int UNROLL>
@@ -257,8 +315,9 @@ static int clamp_threads(int t) {
   return (t / 32) * 32;
 }
 
-// Work-distribution descriptor for one launch.  Dynamic: the grab counter lives at
-// d_counter[8] (its own 64-byte line) and is zeroed on the launching stream first.
+// Work-distribution descriptor for one launch of a GENERIC kernel.  Dynamic: the grab counter
+// lives at d_counter[kGenericGrab] (its own 64-byte line) and is zeroed on the launching stream
+// first.  (The default fast kernels reset their own counters: GrabCtl.)
 static int make_sched(ScrubEngine* e, const Shape& sh, uint64_t body_bytes, uint64_t tile_bytes, bool tma,
                       cudaStream_t st, Sched* out) {
   out->counter = nullptr;
@@ -271,8 +330,8 @@ static int make_sched(ScrubEngine* e, const Shape& sh, uint64_t body_bytes, uint
   out->ntiles = tile_bytes ? body_bytes / tile_bytes : 0;
   out->nchunks = out->ntiles;
   if (sh.schedule != 2 && sh.schedule != 3) return CCM_OK;
-  CCM_CUDA(cudaMemsetAsync(e->d_counter + 8, 0, sizeof(unsigned long long), st));
-  out->counter = e->d_counter + 8;
+  CCM_CUDA(cudaMemsetAsync(e->d_counter + kGenericGrab, 0, sizeof(unsigned long long), st));
+  out->counter = e->d_counter + kGenericGrab;
   if (tma) {
     out->chunk_tiles = sh.unroll > 0 ? (uint32_t)sh.unroll : 4;
   } else {
@@ -284,9 +343,37 @@ static int make_sched(ScrubEngine* e, const Shape& sh, uint64_t body_bytes, uint
   return CCM_OK;
 }
 
-// Scrub one contiguous range on `st` (no sync).
+// Launch with the programmatic-stream-serialization attribute (CCM_PDL=1): the kernel may be
+// scheduled while the previous kernel on the stream drains; it blocks in griddepcontrol.wait
+// until that kernel has completed and flushed, so ordering is unchanged.
+static bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("CCM_PDL"); return v && *v && strcmp(v, "0") != 0; }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_fast(void (*kernel)(KArgs...), int grid, int threads, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof lc);
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3((unsigned)threads);
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, kernel, KArgs(args)...);
+}
+
+// True when (variant, cfg) resolves to the compile-time-shape default kernel.
+static bool is_fast_scrub(int variant, const ccm_launch_cfg* cfg) {
+  return cfg == nullptr && resolve_scrub_variant(variant) == CCM_SCRUB_ST256;
+}
+
+// Scrub one contiguous range on `st` (no sync).  zero_on_exit: see scrub_st256_fast_kernel
+// (honoured by the default kernel only — callers check is_fast_scrub()).
 static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const ccm_launch_cfg* cfg,
-                       cudaStream_t st) {
+                       cudaStream_t st, unsigned long long* zero_on_exit = nullptr) {
   if (n == 0) return CCM_OK;
   variant = resolve_scrub_variant(variant);
   Shape sh = scrub_shape(variant, cfg);
@@ -312,11 +399,8 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
       if (cfg == nullptr) {
         // library default: compile-time shape (148 persistent CTAs x 512 threads, 8 x STG.256 per
         // thread per 128 KiB grab) — scrub_st256_fast_kernel
-        constexpr int kThreads = 512, kPer = 8;
-        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)kThreads * kPer * 32);
-        CCM_CUDA(cudaMemsetAsync(e->d_counter + 8, 0, sizeof(unsigned long long), st));
-        scrub_st256_fast_kernel<kThreads, kPer, kPolDefault><<<e->sm_count, kThreads, 0, st>>>(s, nchunks, e->d_counter + 8);
-        err = cudaGetLastError();
+        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)kFastScrubThreads * kFastScrubPer * 32);
+        err = launch_fast(CCM_FAST_SCRUB, e->sm_count, kFastScrubThreads, st, s, nchunks, e->scrub_ctl(), zero_on_exit);
         g_launches++;
         break;
       }
@@ -368,7 +452,7 @@ static int verify_range(ScrubEngine* e, const void* p, uint64_t n, int variant, 
   variant = resolve_verify_variant(variant);
   Shape sh = verify_shape(variant, cfg);
   sh.threads = clamp_threads(sh.threads);
-  if (variant != CCM_VERIFY_TMA && sh.unroll != 1 && sh.unroll != 2 && sh.unroll != 8) sh.unroll = 4;
+  if (sh.unroll != 1 && sh.unroll != 2 && sh.unroll != 8) sh.unroll = 4;
   const int grid = e->sm_count * (sh.ctas_per_sm > 0 ? sh.ctas_per_sm : 1);
   cudaError_t err = cudaSuccess;
   switch (variant) {
@@ -384,33 +468,13 @@ static int verify_range(ScrubEngine* e, const void* p, uint64_t n, int variant, 
       if (cfg == nullptr) {
         // library default: 148 persistent CTAs x 1024 threads, 4 x LDG.256 in flight per thread
         // per 128 KiB grab — verify_ld256_fast_kernel
-        constexpr int kThreads = 1024, kPer = 4;
-        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)kThreads * kPer * 32);
-        CCM_CUDA(cudaMemsetAsync(e->d_counter + 8, 0, sizeof(unsigned long long), st));
-        verify_ld256_fast_kernel<kThreads, kPer, kPolStreaming><<<e->sm_count, kThreads, 0, st>>>(
-            s, nchunks, e->d_counter + 8, e->d_counter);
-        err = cudaGetLastError();
+        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)kFastVerifyThreads * kFastVerifyPer * 32);
+        err = launch_fast(CCM_FAST_VERIFY, e->sm_count, kFastVerifyThreads, st, s, nchunks, e->verify_ctl(), e->d_counter);
         break;
       }
       Sched sc;
       if (int rc = make_sched(e, sh, s.body_vecs * 32, (uint64_t)sh.threads * sh.unroll * 32, false, st, &sc)) return rc;
       err = launch_verify_ld<32>(s, grid, sh, e->d_counter, sc, st);
-      break;
-    }
-    case CCM_VERIFY_TMA: {
-      RegionSplit s = split_region(p, n, 16, 128);
-      constexpr int STAGES = 4;
-      uint32_t tile = (uint32_t)sh.tile_bytes & ~127u;
-      if (tile < 1024) tile = 1024;
-      const size_t maxsm = (e->smem_optin - 2048) / (size_t)sh.ctas_per_sm;
-      if ((size_t)tile * STAGES > maxsm) tile = (uint32_t)((maxsm / STAGES) & ~127ull);
-      int threads = sh.threads < 64 ? 64 : sh.threads;
-      err = cudaFuncSetAttribute(verify_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(tile * STAGES));
-      if (err == cudaSuccess) {
-        verify_tma_kernel<STAGES><<<grid, threads, tile * STAGES, st>>>(s, tile, e->d_counter);
-        err = cudaGetLastError();
-      }
       break;
     }
     default:
@@ -436,6 +500,7 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
 
 int engine_arena_release(ScrubEngine* e, double* ms) {
   std::lock_guard<std::mutex> g(e->mu);
+  if (!e->ready) { e->segs.clear(); e->arena_bytes = 0; if (ms) *ms = 0; return CCM_OK; }  // torn down: nothing held
   const double t0 = now_ms();
   CCM_CUDA(cudaSetDevice(e->ordinal));
   int rc = CCM_OK;
@@ -451,7 +516,9 @@ int engine_arena_release(ScrubEngine* e, double* ms) {
 
 int engine_arena_acquire(ScrubEngine* e, uint64_t bytes, ccm_arena_info* out) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   if (!e->segs.empty()) { set_error("arena already held on CUDA device %d", e->ordinal); return CCM_ERR_STATE; }
+  e->join_reaper();  // HBM of the previous gate must be back before "all free HBM" is measured
   const double t0 = now_ms();
   CCM_CUDA(cudaSetDevice(e->ordinal));
   size_t fr = 0, tot = 0;
@@ -511,6 +578,7 @@ static int need_arena(ScrubEngine* e) {
 
 int engine_arena_scrub(ScrubEngine* e, int variant, const ccm_launch_cfg* cfg, void* stream, float* ms) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   int rc = need_arena(e); if (rc) return rc;
   CCM_CUDA(cudaSetDevice(e->ordinal));
   cudaStream_t st = e->pick(stream);
@@ -534,6 +602,7 @@ static int fetch_count_locked(ScrubEngine* e, cudaStream_t st, uint64_t* nonzero
 int engine_arena_verify(ScrubEngine* e, int variant, const ccm_launch_cfg* cfg, void* stream,
                         uint64_t* nonzero, float* ms) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   int rc = need_arena(e); if (rc) return rc;
   CCM_CUDA(cudaSetDevice(e->ordinal));
   cudaStream_t st = e->pick(stream);
@@ -549,13 +618,20 @@ int engine_arena_verify(ScrubEngine* e, int variant, const ccm_launch_cfg* cfg, 
 int engine_arena_scrub_verify_async(ScrubEngine* e, int sv, int vv, const ccm_launch_cfg* scfg,
                                     const ccm_launch_cfg* vcfg, void* stream) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   int rc = need_arena(e); if (rc) return rc;
   CCM_CUDA(cudaSetDevice(e->ordinal));
   cudaStream_t st = e->pick(stream);
   cudaEvent_t* evs = e->step_count < kMaxSteps ? e->step_ev[e->step_count] : nullptr;
   if (evs) CCM_CUDA(cudaEventRecord(evs[0], st));
-  for (auto& s : e->segs) { rc = scrub_range(e, s.ptr, s.bytes, sv, scfg, st); if (rc) return rc; }
-  CCM_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st));
+  // Default kernels: the scrub's last CTA also clears the verify counter, so one step is
+  // exactly two kernel nodes per segment and no memset nodes.
+  const bool fast = is_fast_scrub(sv, scfg);
+  for (auto& s : e->segs) {
+    rc = scrub_range(e, s.ptr, s.bytes, sv, scfg, st, fast ? e->d_counter : nullptr);
+    if (rc) return rc;
+  }
+  if (!fast) CCM_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st));
   if (evs) CCM_CUDA(cudaEventRecord(evs[1], st));
   for (auto& s : e->segs) { rc = verify_range(e, s.ptr, s.bytes, vv, vcfg, st); if (rc) return rc; }
   if (evs) { CCM_CUDA(cudaEventRecord(evs[2], st)); e->step_count++; }
@@ -564,6 +640,7 @@ int engine_arena_scrub_verify_async(ScrubEngine* e, int sv, int vv, const ccm_la
 
 int engine_arena_step_times(ScrubEngine* e, int cap, float* scrub_ms, float* verify_ms, int* n) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   CCM_CUDA(cudaSetDevice(e->ordinal));
   int k = e->step_count < cap ? e->step_count : cap;
   for (int i = 0; i < k; ++i) {
@@ -578,6 +655,7 @@ int engine_arena_step_times(ScrubEngine* e, int cap, float* scrub_ms, float* ver
 
 int engine_arena_fetch_count(ScrubEngine* e, void* stream, uint64_t* nonzero) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   CCM_CUDA(cudaSetDevice(e->ordinal));
   return fetch_count_locked(e, e->pick(stream), nonzero);
 }
@@ -591,6 +669,7 @@ __global__ void fill_byte_kernel(uint4* p, uint64_t nvec, uint32_t word) {
 
 int engine_arena_fill(ScrubEngine* e, int byte_value, void* stream) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   int rc = need_arena(e); if (rc) return rc;
   CCM_CUDA(cudaSetDevice(e->ordinal));
   cudaStream_t st = e->pick(stream);
@@ -609,6 +688,7 @@ int engine_arena_fill(ScrubEngine* e, int byte_value, void* stream) {
 
 int engine_arena_fill_random(ScrubEngine* e, uint64_t seed, void* stream) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   int rc = need_arena(e); if (rc) return rc;
   CCM_CUDA(cudaSetDevice(e->ordinal));
   cudaStream_t st = e->pick(stream);
@@ -627,6 +707,7 @@ int engine_arena_fill_random(ScrubEngine* e, uint64_t seed, void* stream) {
 
 int engine_arena_rw(ScrubEngine* e, uint64_t offset, void* host, uint64_t bytes, bool write) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   int rc = need_arena(e); if (rc) return rc;
   if (offset + bytes > e->arena_bytes || offset + bytes < offset) {
     set_error("arena access [%llu,+%llu) outside %llu bytes", (unsigned long long)offset,
@@ -687,19 +768,48 @@ static const VmmApi& vmm() {
   return api;
 }
 
-struct VmmChunk { uint64_t off, bytes; CUmemGenericAllocationHandle handle; cudaEvent_t verified; };
+// Hands a mapping back to the driver: unmap, release every physical chunk, free the range.
+// (One cuMemUnmap over the whole range: per-chunk unmaps are 10x slower, and so is unmapping
+// under a running kernel — benchmarks/vmm_probe.cu, profiles/r2_vmm_probe_1gpu.log.)
+static double give_back(const VmmApi& api, VmmMapping& m) {
+  const double t0 = now_ms();
+  if (m.mapped) api.Unmap(m.base, m.mapped);
+  for (auto h : m.handles) api.Release(h);
+  if (m.base) api.AddressFree(m.base, m.va_bytes);
+  m = VmmMapping();
+  return now_ms() - t0;
+}
+
+static bool async_release_enabled() { return env_u64("CCM_ASYNC_RELEASE", 1) != 0; }
 
 // Pipelined scrub-and-verify over freshly mapped HBM.  Returns CCM_ERR_UNSUPPORTED when
 // the VMM path cannot be used at all (caller falls back to the arena path).
-static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* r) {
+//
+//   host    : create+map+access chunk 0 | chunk 1 | chunk 2 | ...            | D2H count, verdict
+//   stream  :                    scrub 0, verify 0 | scrub 1, verify 1 | ...
+//   reaper  :                                                                  unmap + release
+//
+// * chunk sizes grow 1, 2, 4, 8, 16, 16, ... GiB so the first stores are issued ~1 ms into the
+//   call; a few large chunks keep the driver's per-mapping costs (unmap!) down;
+// * with bytes == 0 the last CCM_ARENA_RESERVE_MB of free HBM (the "tail zone") are taken in
+//   32 MiB -> 2 MiB granules until the driver says out-of-memory, so the region is everything
+//   the context can reach, not "free minus a safety margin";
+// * every chunk is read back right after it was zeroed, while the host is still mapping the
+//   next one (the GPU would otherwise idle: mapping 16 GiB takes as long as scrubbing it);
+// * the verdict is returned as soon as the 8-byte count is on the host; cuMemUnmap/cuMemRelease
+//   (0.33 ms/GiB, serialised node-wide by the driver) run on the engine's reaper thread.
+static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t inject, ccm_scrub_result* r) {
   const VmmApi& api = vmm();
   if (!api.ok) return CCM_ERR_UNSUPPORTED;
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   if (!e->segs.empty()) { set_error("arena already held on CUDA device %d", e->ordinal); return CCM_ERR_STATE; }
+  r->ms_release_wait = e->join_reaper();
   CCM_CUDA(cudaSetDevice(e->ordinal));
   size_t fr = 0, tot = 0;
   CCM_CUDA(cudaMemGetInfo(&fr, &tot));
   r->device_total_bytes = tot;
+  r->device_free_before = fr;
   CUmemAllocationProp prop;
   memset(&prop, 0, sizeof prop);
   prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
@@ -709,99 +819,161 @@ static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, ccm_scrub_resu
   if (api.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
     return CCM_ERR_UNSUPPORTED;
   const bool want_max = (bytes == 0);
-  const uint64_t reserve = env_u64("CCM_ARENA_RESERVE_MB", 256) * kMiB;
-  uint64_t want = want_max ? (fr > reserve ? fr - reserve : 0) : bytes;
   // physical memory comes in `gran` units; an exact request is rounded UP and the
   // surplus bytes are scrubbed too (harmless, and they are ours).
-  const uint64_t va_bytes = want_max ? want / gran * gran : (want + gran - 1) / gran * gran;
+  const uint64_t va_bytes = want_max ? (uint64_t)fr / gran * gran : (bytes + gran - 1) / gran * gran;
   if (va_bytes == 0) { set_error("no free HBM to scrub (free=%zu)", fr); return CCM_ERR_NOMEM; }
-  uint64_t chunk = env_u64("CCM_VMM_CHUNK_MB", 16384) * kMiB / gran * gran;
+  // tail zone: where running out of memory is expected and simply ends the region
+  uint64_t tail_zone = want_max ? env_u64("CCM_ARENA_RESERVE_MB", 256) * kMiB / gran * gran : 0;
+  if (tail_zone > va_bytes) tail_zone = va_bytes;
+  uint64_t main_end = va_bytes - tail_zone;
+  uint64_t max_chunk = env_u64("CCM_VMM_CHUNK_MB", 16384) * kMiB / gran * gran;
+  if (max_chunk < gran) max_chunk = gran;
+  uint64_t chunk = env_u64("CCM_VMM_FIRST_CHUNK_MB", 1024) * kMiB / gran * gran;
   if (chunk < gran) chunk = gran;
+  if (chunk > max_chunk) chunk = max_chunk;
+  uint64_t tail_chunk = 32 * kMiB / gran * gran;
+  if (tail_chunk < gran) tail_chunk = gran;
+  const bool interleave = env_u64("CCM_INTERLEAVE_VERIFY", 1) != 0;
 
-  CUdeviceptr base = 0;
-  if (api.AddressReserve(&base, va_bytes, 0, 0, 0) != CUDA_SUCCESS) return CCM_ERR_UNSUPPORTED;
+  VmmMapping m;
+  if (api.AddressReserve(&m.base, va_bytes, 0, 0, 0) != CUDA_SUCCESS) return CCM_ERR_UNSUPPORTED;
+  m.va_bytes = va_bytes;
   cudaStream_t st = e->stream;
-  std::vector<VmmChunk> chunks;
   CUmemAccessDesc acc;
   memset(&acc, 0, sizeof acc);
   acc.location = prop.location;
   acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
   int rc = CCM_OK;
-  double host_acquire = 0, host_release = 0;
-  uint64_t off = 0;
+  double host_acquire = 0;
+  int timed = 0;  // chunks with an event triple
 
-  // ---- phase A: map chunk i, enqueue its scrub, go on mapping chunk i+1 ----------
+  // enqueue scrub (+ read-back) of [off, off+n) with CUDA events around each kernel
+  auto enqueue = [&](uint64_t off, uint64_t n) -> int {
+    cudaEvent_t* evs = timed < kMaxPipeChunks ? e->pipe_ev[timed] : nullptr;
+    if (evs) cudaEventRecord(evs[0], st);
+    int rc2 = scrub_range(e, (void*)(m.base + off), n, CCM_SCRUB_AUTO, nullptr, st);
+    if (evs) cudaEventRecord(evs[1], st);
+    if (inject) {  // fault drill: dirty bytes the read-back below MUST find
+      const uint64_t cand[4] = {off, off + 17 < off + n ? off + 17 : off, off + n / 2 + 3 < off + n ? off + n / 2 + 3 : off, off + n - 1};
+      for (int i = 0; i < 4 && inject; ++i) {
+        bool dup = false;
+        for (int j = 0; j < i; ++j) dup |= cand[j] == cand[i];
+        if (dup) continue;
+        cudaMemsetAsync((void*)(m.base + cand[i]), 0xA5, 1, st);
+        --inject;
+      }
+    }
+    if (rc2 == CCM_OK && interleave) rc2 = verify_range(e, (const void*)(m.base + off), n, CCM_VERIFY_AUTO, nullptr, st);
+    if (evs) { cudaEventRecord(evs[2], st); ++timed; }
+    return rc2;
+  };
+
+  if (cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st) != cudaSuccess) rc = CCM_ERR_CUDA;
   cudaEventRecord(e->ev[0], st);
+  uint64_t off = 0, tail_start = 0;
+  bool in_tail = false;
   while (off < va_bytes && rc == CCM_OK) {
-    uint64_t n = va_bytes - off < chunk ? va_bytes - off : chunk;
+    if (!in_tail && off >= main_end) { in_tail = true; tail_start = off; }
+    const uint64_t limit = in_tail ? va_bytes : main_end;
+    uint64_t& ck = in_tail ? tail_chunk : chunk;
+    const uint64_t n = limit - off < ck ? limit - off : ck;
     const double t0 = now_ms();
     CUmemGenericAllocationHandle h;
     CUresult cr = api.Create(&h, n, &prop, 0);
-    if (cr == CUDA_ERROR_OUT_OF_MEMORY && chunk > 64 * kMiB && chunk > gran) {
-      chunk = (chunk / 2) / gran * gran;  // fragmented / less free than reported: try smaller pieces
-      if (chunk < gran) chunk = gran;
-      continue;
+    if (cr == CUDA_ERROR_OUT_OF_MEMORY) {
+      const uint64_t floor_bytes = in_tail ? gran : (64 * kMiB > gran ? 64 * kMiB : gran);
+      if (ck > floor_bytes) { ck = (ck / 2) / gran * gran; if (ck < gran) ck = gran; continue; }  // fragmented / less free than reported
+      if (want_max && !in_tail) { main_end = off; continue; }  // less free than reported: finish in small granules
+      if (want_max && off > 0) break;  // take what there is
     }
-    if (cr == CUDA_ERROR_OUT_OF_MEMORY && want_max && off > 0) break;  // take what there is
-    if (cr != CUDA_SUCCESS) { set_error("cuMemCreate(%llu) failed: %d", (unsigned long long)n, (int)cr); rc = cr == CUDA_ERROR_OUT_OF_MEMORY ? CCM_ERR_NOMEM : CCM_ERR_CUDA; break; }
-    CUresult mr = api.Map(base + off, n, 0, h, 0);
-    if (mr == CUDA_SUCCESS) mr = api.SetAccess(base + off, n, &acc, 1);
+    if (cr != CUDA_SUCCESS) {
+      set_error("cuMemCreate(%llu) failed: %d", (unsigned long long)n, (int)cr);
+      rc = cr == CUDA_ERROR_OUT_OF_MEMORY ? CCM_ERR_NOMEM : CCM_ERR_CUDA;
+      break;
+    }
+    CUresult mr = api.Map(m.base + off, n, 0, h, 0);
+    if (mr == CUDA_SUCCESS) {
+      mr = api.SetAccess(m.base + off, n, &acc, 1);
+      if (mr != CUDA_SUCCESS) api.Unmap(m.base + off, n);
+    }
     if (mr != CUDA_SUCCESS) {
       api.Release(h);
+      if (mr == CUDA_ERROR_OUT_OF_MEMORY && in_tail) break;  // no room left for page tables: the region ends here
       set_error("cuMemMap/cuMemSetAccess failed: %d", (int)mr);
       rc = CCM_ERR_CUDA;
       break;
     }
     host_acquire += now_ms() - t0;
-    chunks.push_back(VmmChunk{off, n, h, nullptr});
-    if (rc == CCM_OK) rc = scrub_range(e, (void*)(base + off), n, CCM_SCRUB_AUTO, nullptr, st);
+    m.handles.push_back(h);
+    m.mapped = off + n;
+    // tail-zone granules are scrubbed with ONE launch pair once the zone is mapped
+    if (!in_tail) rc = enqueue(off, n);
     off += n;
+    if (!in_tail && chunk < max_chunk) { chunk *= 2; if (chunk > max_chunk) chunk = max_chunk; }
   }
-  const uint64_t mapped = off;
-  cudaEventRecord(e->ev[1], st);
-
-  // ---- phase B: ONE verify launch over the contiguous range, then give it all back --
-  // (Unmapping chunk i while later chunks are still being verified was measured and
-  // rejected: cuMemUnmap under a running kernel costs 4-40 ms per chunk; after the
-  // stream has drained the whole teardown is ~60 ms for 190 GB.)
-  if (rc == CCM_OK) {
-    if (cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st) != cudaSuccess) rc = CCM_ERR_CUDA;
-    if (rc == CCM_OK) rc = verify_range(e, (const void*)base, mapped, CCM_VERIFY_AUTO, nullptr, st);
-    cudaEventRecord(e->ev[2], st);
-    if (rc == CCM_OK &&
-        cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) != cudaSuccess)
-      rc = CCM_ERR_CUDA;
+  if (rc == CCM_OK && in_tail && m.mapped > tail_start) rc = enqueue(tail_start, m.mapped - tail_start);
+  if (rc == CCM_OK && !interleave) {
+    cudaEventRecord(e->ev[1], st);
+    rc = verify_range(e, (const void*)m.base, m.mapped, CCM_VERIFY_AUTO, nullptr, st);
   }
+  cudaEventRecord(e->ev[2], st);
+  if (rc == CCM_OK &&
+      cudaMemcpyAsync(e->h_counter, e->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    rc = CCM_ERR_CUDA;
   cudaError_t serr = cudaStreamSynchronize(st);  // nothing may still touch the mapping below
-  {
-    const double t0 = now_ms();
-    if (mapped) api.Unmap(base, mapped);
-    for (auto& c : chunks) {
-      api.Release(c.handle);
-      if (c.verified) cudaEventDestroy(c.verified);
-    }
-    api.AddressFree(base, va_bytes);
-    host_release = now_ms() - t0;
-  }
   if (rc == CCM_OK && serr != cudaSuccess) { set_error("stream sync failed: %s", cudaGetErrorString(serr)); rc = CCM_ERR_CUDA; }
-  if (rc != CCM_OK) return rc;
 
-  float ms_s = 0, ms_v = 0;
-  cudaEventElapsedTime(&ms_s, e->ev[0], e->ev[1]);
-  cudaEventElapsedTime(&ms_v, e->ev[1], e->ev[2]);
-  r->bytes_scrubbed = mapped;
-  r->segments = (int)chunks.size();
-  r->ms_acquire = host_acquire;   // host time inside create/map/set-access (overlapped with the scrub)
-  r->ms_release = host_release;   // unmap + release + address-free after the stream drained
-  r->ms_scrub = ms_s;             // first scrub launch .. last scrub done (includes waiting for mappings)
-  r->ms_verify = ms_v;
-  r->nonzero_bytes = (uint64_t)*e->h_counter;
+  const uint64_t mapped = m.mapped;
+  const int nchunks = (int)m.handles.size();
+  if (rc == CCM_OK) {
+    float span = 0, ms_s = 0, ms_v = 0;
+    cudaEventElapsedTime(&span, e->ev[0], e->ev[2]);
+    for (int i = 0; i < timed; ++i) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, e->pipe_ev[i][0], e->pipe_ev[i][1]);
+      cudaEventElapsedTime(&b, e->pipe_ev[i][1], e->pipe_ev[i][2]);
+      ms_s += a;
+      ms_v += b;
+    }
+    if (!interleave) cudaEventElapsedTime(&ms_v, e->ev[1], e->ev[2]);
+    r->bytes_scrubbed = mapped;
+    r->bytes_unreached = want_max && (uint64_t)fr > mapped ? (uint64_t)fr - mapped : 0;
+    r->segments = nchunks;
+    r->ms_acquire = host_acquire;
+    r->ms_scrub = ms_s;
+    r->ms_verify = ms_v;
+    r->ms_gpu_span = span;
+    r->nonzero_bytes = (uint64_t)*e->h_counter;
+  }
+  // ---- give the HBM back: on the reaper (default) or right here -----------------------
+  if (rc == CCM_OK && async_release_enabled()) {
+    r->release_deferred = 1;
+    r->ms_release = 0;
+    e->reaper_failed = false;
+    const int ordinal = e->ordinal;
+    e->reaper = std::thread([e, ordinal, mm = std::move(m)]() mutable {
+      cudaSetDevice(ordinal);
+      e->reaper_ms = give_back(vmm(), mm);  // read only after join()
+    });
+  } else {
+    r->ms_release = give_back(api, m);
+  }
+  if (rc != CCM_OK) return rc;
   if (!want_max && mapped < bytes) { set_error("mapped only %llu of %llu bytes", (unsigned long long)mapped, (unsigned long long)bytes); return CCM_ERR_NOMEM; }
   return CCM_OK;
 }
 
+int engine_release_wait(ScrubEngine* e, double* ms_release, double* ms_waited) {
+  std::lock_guard<std::mutex> g(e->mu);
+  const double w = e->join_reaper();
+  if (ms_release) *ms_release = e->reaper_ms;
+  if (ms_waited) *ms_waited = w;
+  return CCM_OK;
+}
+
 // --------------------------------------------------------------- product call
-int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* out) {
+int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, uint64_t inject, ccm_scrub_result* out) {
   const double t0 = now_ms();
   ccm_scrub_result r;
   memset(&r, 0, sizeof r);
@@ -810,7 +982,7 @@ int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* out) {
   r.scrub_variant = resolve_scrub_variant(CCM_SCRUB_AUTO);
   r.verify_variant = resolve_verify_variant(CCM_VERIFY_AUTO);
   int rc = CCM_ERR_UNSUPPORTED;
-  if (env_u64("CCM_PIPELINE", 1) != 0) rc = scrub_verify_pipelined(e, bytes, &r);
+  if (env_u64("CCM_PIPELINE", 1) != 0) rc = scrub_verify_pipelined(e, bytes, inject, &r);
   if (rc == CCM_ERR_UNSUPPORTED) {
     // plain path: one cudaMalloc'ed arena, whole-arena scrub, whole-arena verify
     ccm_arena_info ai;
@@ -819,6 +991,8 @@ int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* out) {
       r.ms_acquire = ai.ms_acquire;
       r.bytes_scrubbed = ai.bytes;
       r.device_total_bytes = ai.device_total_bytes;
+      r.device_free_before = ai.device_free_before;
+      r.bytes_unreached = bytes == 0 && ai.device_free_before > ai.bytes ? ai.device_free_before - ai.bytes : 0;
       r.segments = ai.segments;
       float ms_s = 0, ms_v = 0;
       uint64_t nz = 0;
@@ -836,6 +1010,7 @@ int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* out) {
     rc = CCM_ERR_DIRTY;
   }
   r.ms_total = now_ms() - t0;
+  r.sm_count = e->sm_count;
   r.status = rc;
   if (out) *out = r;
   return rc;
@@ -845,6 +1020,7 @@ int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, ccm_scrub_result* out) {
 int engine_region_scrub(ScrubEngine* e, void* dptr, uint64_t bytes, int variant, const ccm_launch_cfg* cfg,
                         void* stream, float* ms) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   CCM_CUDA(cudaSetDevice(e->ordinal));
   cudaStream_t st = e->pick(stream);
   if (ms) CCM_CUDA(cudaEventRecord(e->ev[0], st));
@@ -861,6 +1037,7 @@ int engine_region_scrub(ScrubEngine* e, void* dptr, uint64_t bytes, int variant,
 int engine_region_verify(ScrubEngine* e, const void* dptr, uint64_t bytes, int variant,
                          const ccm_launch_cfg* cfg, void* stream, uint64_t* nonzero, float* ms) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   CCM_CUDA(cudaSetDevice(e->ordinal));
   cudaStream_t st = e->pick(stream);
   CCM_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), st));
@@ -877,6 +1054,7 @@ int engine_region_verify(ScrubEngine* e, const void* dptr, uint64_t bytes, int v
 int engine_host_roundtrip(ScrubEngine* e, void* host_buf, uint64_t bytes, uint64_t dev_offset,
                           int sv, int vv, uint64_t* pre, uint64_t* post) {
   std::lock_guard<std::mutex> g(e->mu);
+  CCM_ENSURE_READY(e);
   CCM_CUDA(cudaSetDevice(e->ordinal));
   cudaStream_t st = e->stream;
   uint8_t* d = nullptr;

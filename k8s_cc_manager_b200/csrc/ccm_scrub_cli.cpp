@@ -67,12 +67,14 @@ int main(int argc, char** argv) {
     clean = clean && r.status == CCM_OK && r.nonzero_bytes == 0;
     printf("%s{\"bdf\": \"%s\", \"bytes_requested\": %llu, \"bytes_scrubbed\": %llu, \"device_total_bytes\": %llu, "
            "\"nonzero_bytes\": %llu, \"ms_acquire\": %.3f, \"ms_scrub\": %.3f, \"ms_verify\": %.3f, \"ms_release\": %.3f, "
-           "\"ms_total\": %.3f, \"segments\": %d, \"status\": %d}",
+           "\"ms_total\": %.3f, \"segments\": %d, \"status\": %d, \"release_deferred\": %d, "
+           "\"device_free_before\": %llu, \"bytes_unreached\": %llu, \"ms_release_wait\": %.3f, \"ms_gpu_span\": %.3f}",
            i ? ", " : "", names[i].c_str(), (unsigned long long)r.bytes_requested, (unsigned long long)r.bytes_scrubbed,
            (unsigned long long)r.device_total_bytes, (unsigned long long)r.nonzero_bytes, r.ms_acquire, r.ms_scrub,
-           r.ms_verify, r.ms_release, r.ms_total, r.segments, r.status);
+           r.ms_verify, r.ms_release, r.ms_total, r.segments, r.status, r.release_deferred,
+           (unsigned long long)r.device_free_before, (unsigned long long)r.bytes_unreached, r.ms_release_wait, r.ms_gpu_span);
   }
   printf("]}\n");
-  for (int d : devs) ccm_device_release(d);
+  ccm_device_release_many((int)devs.size(), devs.data(), nullptr);  // joins the deferred HBM release, drops the contexts
   return clean ? 0 : 3;
 }

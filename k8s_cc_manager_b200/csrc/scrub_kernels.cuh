@@ -21,8 +21,9 @@
 //   scrub_st256_fast_kernel / verify_ld256_fast_kernel   what AUTO launches (compile-time shape)
 //   scrub_st_kernel / verify_ld_kernel                   any shape / width / policy / schedule
 //   scrub_tma_kernel                                     cp.async.bulk stores from one zero tile
-//   verify_tma_kernel                                    cp.async.bulk loads into an mbarrier ring
 //   fill_pattern_kernel                                  seeded test pattern (tests only)
+// (Round 1 also carried a TMA bulk-LOAD verify ring; it never beat LDG.256 in speed or power and
+// was the only kernel with an open racecheck finding, so it was removed — DESIGN.md §5.)
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -234,20 +235,49 @@ scrub_st_kernel(RegionSplit s, Sched sched) {
 // chunk and ~10 instructions of bookkeeping, instead of ~13 instructions per store in the
 // generic kernel (runtime stride => a 64-bit add pair per access).  Same GB/s — the kernels
 // are egress / DRAM bound — fewer issued instructions, less power.
+//
+// Launch bookkeeping lives IN the kernel (round 2): the grab counter is handed back zeroed by
+// the last CTA to finish (GrabCtl below), so a step is two kernel nodes and nothing else — no
+// cudaMemsetAsync nodes in front of each launch, which cost ~2-4 us apiece and showed at the
+// 1 GB end of the region sweep.  griddepcontrol.wait / launch_dependents let the host chain the
+// two kernels with programmatic dependent launch (no-ops when launched the ordinary way).
+struct GrabCtl {
+  unsigned long long* grab;  // next chunk index; 0 before and after every launch
+  unsigned long long* done;  // CTAs that have stopped grabbing; 0 before and after every launch
+};
+
+// One thread per CTA calls this after the CTA's last grab returned: the CTA that arrives last
+// knows nobody will touch `grab` again and resets both words for the next launch on the stream.
+__device__ __forceinline__ void grab_release(const GrabCtl& g, unsigned long long* also_zero) {
+  __threadfence();
+  if (atomicAdd(g.done, 1ull) == (unsigned long long)gridDim.x - 1) {
+    *g.grab = 0;
+    *g.done = 0;
+    if (also_zero) *also_zero = 0;
+    __threadfence();
+  }
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// zero_on_exit (may be null): a word the last CTA clears as well — the arena step passes the
+// verify counter, so "scrub" also resets the verdict of the previous read-back.
 template <int THREADS, int PER_THREAD, int POL>
 __global__ void __launch_bounds__(THREADS)
-scrub_st256_fast_kernel(RegionSplit s, uint64_t nchunks, unsigned long long* grab) {
+scrub_st256_fast_kernel(RegionSplit s, uint64_t nchunks, GrabCtl ctl, unsigned long long* zero_on_exit) {
   constexpr uint64_t kChunk = (uint64_t)THREADS * PER_THREAD * 32;
   uint8_t* body = s.base + s.head;
   __shared__ unsigned long long s_chunk[2];
-  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(grab, 1ull);
+  pdl_wait();
+  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(ctl.grab, 1ull);
   __syncthreads();
   int buf = 0;
   for (;;) {
     const uint64_t c = s_chunk[buf];
     if (c >= nchunks) break;
     unsigned long long nxt = 0;
-    if (threadIdx.x == 0) nxt = atomicAdd(grab, 1ull);  // next grab in flight while we store
+    if (threadIdx.x == 0) nxt = atomicAdd(ctl.grab, 1ull);  // next grab in flight while we store
     uint8_t* p = body + c * kChunk + threadIdx.x * 32u;
 #pragma unroll
     for (int u = 0; u < PER_THREAD; ++u) st_zero32<POL>(p + (uint32_t)u * THREADS * 32u);
@@ -255,6 +285,8 @@ scrub_st256_fast_kernel(RegionSplit s, uint64_t nchunks, unsigned long long* gra
     __syncthreads();
     buf ^= 1;
   }
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) grab_release(ctl, zero_on_exit);
   // vectors after the last whole chunk (< kChunk bytes), then the ragged head / tail bytes
   for (uint64_t i = nchunks * (kChunk / 32) + (uint64_t)blockIdx.x * THREADS + threadIdx.x;
        i < s.body_vecs; i += (uint64_t)gridDim.x * THREADS)
@@ -468,19 +500,20 @@ verify_ld_kernel(RegionSplit s, unsigned long long* counter, Sched sched) {
 
 template <int THREADS, int PER_THREAD, int POL>
 __global__ void __launch_bounds__(THREADS)
-verify_ld256_fast_kernel(RegionSplit s, uint64_t nchunks, unsigned long long* grab, unsigned long long* counter) {
+verify_ld256_fast_kernel(RegionSplit s, uint64_t nchunks, GrabCtl ctl, unsigned long long* counter) {
   constexpr uint64_t kChunk = (uint64_t)THREADS * PER_THREAD * 32;
   const uint8_t* body = s.base + s.head;
   uint64_t cnt = 0;
   __shared__ unsigned long long s_chunk[2];
-  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(grab, 1ull);
+  pdl_wait();
+  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(ctl.grab, 1ull);
   __syncthreads();
   int buf = 0;
   for (;;) {
     const uint64_t c = s_chunk[buf];
     if (c >= nchunks) break;
     unsigned long long nxt = 0;
-    if (threadIdx.x == 0) nxt = atomicAdd(grab, 1ull);
+    if (threadIdx.x == 0) nxt = atomicAdd(ctl.grab, 1ull);
     const uint8_t* p = body + c * kChunk + threadIdx.x * 32u;
     Vec32 v[PER_THREAD];
 #pragma unroll
@@ -502,6 +535,8 @@ verify_ld256_fast_kernel(RegionSplit s, uint64_t nchunks, unsigned long long* gr
     __syncthreads();
     buf ^= 1;
   }
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) grab_release(ctl, nullptr);
   for (uint64_t i = nchunks * (kChunk / 32) + (uint64_t)blockIdx.x * THREADS + threadIdx.x;
        i < s.body_vecs; i += (uint64_t)gridDim.x * THREADS) {
     Vec32 v = ld32<POL>(body + i * 32);
@@ -512,98 +547,6 @@ verify_ld256_fast_kernel(RegionSplit s, uint64_t nchunks, unsigned long long* gr
     for (uint64_t i = threadIdx.x; i < s.head; i += THREADS) cnt += (s.base[i] != 0);
     const uint8_t* t = body + s.body_vecs * 32;
     for (uint64_t i = threadIdx.x; i < s.tail; i += THREADS) cnt += (t[i] != 0);
-  }
-  block_accumulate(cnt, counter);
-}
-
-// ------------------------------------------------- verify (TMA bulk-load ring)
-// Producer lane streams cp.async.bulk.shared::cluster.global tiles into a
-// STAGES-deep smem ring (mbarrier complete_tx); all warps consume a stage with
-// 128-bit LDS, OR-reduce, and release it through an "empty" mbarrier.
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-               ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@!p bra W_%=;\n\t}"
-      ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-}
-
-template <int STAGES>
-__global__ void __launch_bounds__(1024)
-verify_tma_kernel(RegionSplit s /* VB = 16 */, uint32_t tile_bytes, unsigned long long* counter) {
-  extern __shared__ __align__(128) uint8_t ring[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t nconsumer_warps = (blockDim.x >> 5) - 1;  // warp 0 is the producer
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], nconsumer_warps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const uint8_t* body = s.base + s.head;
-  const uint64_t body_bytes = s.body_vecs * 16;
-  const uint64_t ntiles = (body_bytes + tile_bytes - 1) / tile_bytes;  // last may be partial
-  // tiles owned by this CTA: blockIdx.x, +gridDim.x, ...
-  const uint64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  uint64_t cnt = 0;
-
-  auto tile_len = [&](uint64_t t) -> uint32_t {
-    uint64_t rem = body_bytes - t * (uint64_t)tile_bytes;
-    return rem < tile_bytes ? (uint32_t)rem : tile_bytes;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (uint64_t k = 0; k < my_tiles; ++k) {
-        const uint32_t stg = (uint32_t)(k % STAGES);
-        const uint64_t use = k / STAGES;
-        if (use > 0) mbar_wait(&empty_bar[stg], (uint32_t)((use - 1) & 1));
-        const uint64_t t = blockIdx.x + k * gridDim.x;
-        const uint32_t len = tile_len(t);
-        mbar_expect_tx(&full_bar[stg], len);
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-            ::"r"((uint32_t)__cvta_generic_to_shared(ring + (size_t)stg * tile_bytes)),
-              "l"(body + t * (uint64_t)tile_bytes), "r"(len),
-              "r"((uint32_t)__cvta_generic_to_shared(&full_bar[stg])) : "memory");
-      }
-    }
-  } else {
-    const uint32_t ctid = threadIdx.x - 32, cthreads = blockDim.x - 32;
-    for (uint64_t k = 0; k < my_tiles; ++k) {
-      const uint32_t stg = (uint32_t)(k % STAGES);
-      mbar_wait(&full_bar[stg], (uint32_t)((k / STAGES) & 1));
-      const uint32_t len = tile_len(blockIdx.x + k * gridDim.x);
-      const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)stg * tile_bytes);
-      uint32_t c = 0;
-      for (uint32_t i = ctid; i < len / 16; i += cthreads) {
-        uint4 v = src[i];
-        if (v.x | v.y | v.z | v.w)
-          c += nonzero_bytes_in_word(v.x) + nonzero_bytes_in_word(v.y) +
-               nonzero_bytes_in_word(v.z) + nonzero_bytes_in_word(v.w);
-      }
-      cnt += c;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stg]);
-    }
-  }
-  if (blockIdx.x == 0) {
-    for (uint64_t i = threadIdx.x; i < s.head; i += blockDim.x) cnt += (s.base[i] != 0);
-    const uint8_t* t = body + body_bytes;
-    for (uint64_t i = threadIdx.x; i < s.tail; i += blockDim.x) cnt += (t[i] != 0);
   }
   block_accumulate(cnt, counter);
 }

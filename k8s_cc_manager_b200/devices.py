@@ -56,6 +56,11 @@ class ScrubReport:
     ms_total: float
     segments: int
     status: int
+    release_deferred: int = 0        # 1: the HBM is handed back by libccm's background reaper
+    device_free_before: int = 0      # free HBM when the call started
+    bytes_unreached: int = 0         # free HBM that could not be mapped (hence not scrubbed)
+    ms_release_wait: float = 0.0     # waited for the previous call's deferred release
+    ms_gpu_span: float = 0.0         # first scrub launch .. last verify done
 
     @property
     def clean(self) -> bool:
@@ -63,7 +68,14 @@ class ScrubReport:
 
     @property
     def coverage(self) -> float:
+        """Scrubbed fraction of the DEVICE's memory (the rest is the CUDA context's own
+        footprint, driver reservations and whatever other contexts hold)."""
         return self.bytes_scrubbed / self.device_total_bytes if self.device_total_bytes else 0.0
+
+    @property
+    def coverage_of_free(self) -> float:
+        """Scrubbed fraction of what was free when the call started (1.0 = every reachable byte)."""
+        return self.bytes_scrubbed / self.device_free_before if self.device_free_before else 0.0
 
     @property
     def scrub_gbs(self) -> float:
@@ -76,7 +88,8 @@ class ScrubReport:
     @classmethod
     def from_native(cls, bdf: str, r: N.ScrubResult) -> "ScrubReport":
         return cls(bdf, r.bytes_requested, r.bytes_scrubbed, r.device_total_bytes, r.nonzero_bytes,
-                   r.ms_acquire, r.ms_scrub, r.ms_verify, r.ms_release, r.ms_total, r.segments, r.status)
+                   r.ms_acquire, r.ms_scrub, r.ms_verify, r.ms_release, r.ms_total, r.segments, r.status,
+                   r.release_deferred, r.device_free_before, r.bytes_unreached, r.ms_release_wait, r.ms_gpu_span)
 
 
 class NvidiaDevice:
@@ -142,6 +155,13 @@ class NvidiaDevice:
         _check(rc, "scrub_and_verify", self.bdf)
         return ScrubReport.from_native(self.bdf, res)
 
+    def wait_scrub_released(self) -> Tuple[float, float]:
+        """Blocks until the HBM of the last scrub_and_verify() is back with the driver (libccm
+        hands it back on a background thread so the verdict is not held up by cuMemUnmap /
+        cuMemRelease).  Returns (ms the release took, ms this call waited)."""
+        rel, waited = C.c_double(0.0), C.c_double(0.0)
+        _check(N.lib().ccm_scrub_release_wait(self.index, C.byref(rel), C.byref(waited)), "wait_scrub_released", self.bdf)
+        return rel.value, waited.value
 
     def release_cuda_context(self) -> None:
         """Give back everything libccm holds on this GPU, including its CUDA primary context
@@ -190,6 +210,18 @@ def scrub_and_verify_many(devices: Sequence[NvidiaDevice], nbytes: int = 0) -> T
     return [ScrubReport.from_native(d.bdf, res[i]) for i, d in enumerate(devices)], wall.value
 
 
+def release_cuda_contexts(devices: Sequence[NvidiaDevice]) -> float:
+    """Concurrent ccm_device_release for several GPUs (one native thread each): joins each
+    engine's deferred HBM release, then resets its CUDA primary context.  Returns wall ms."""
+    n = len(devices)
+    if n == 0:
+        return 0.0
+    idx = (C.c_int * n)(*[d.index for d in devices])
+    wall = C.c_double(0.0)
+    _check(N.lib().ccm_device_release_many(n, idx, C.byref(wall)), "release_cuda_contexts")
+    return wall.value
+
+
 def select_backend(name: str) -> None:
     """Explicit backend choice ('sim' | 'cudasim' | 'sysfs'); rebuilds the device table."""
     if name not in N.BACKENDS:
@@ -221,6 +253,10 @@ class ScrubbingProxy:
         native = object.__getattribute__(self, "_native")
         if native is not None:
             native.release_cuda_context()
+
+    def wait_scrub_released(self):
+        native = object.__getattribute__(self, "_native")
+        return native.wait_scrub_released() if native is not None else (0.0, 0.0)
 
     def scrub_and_verify(self, nbytes: int = 0) -> ScrubReport:
         native = object.__getattribute__(self, "_native")

@@ -46,8 +46,10 @@ from kubernetes.client.rest import ApiException
 from . import devices as _devices
 from .devices import GpuError
 from .drain_gate import (
+    CC_MODE_STATE_LABEL,
     evict_gpu_operator_components,
     fetch_current_component_labels,
+    recover_journaled_labels,
     reschedule_gpu_operator_components,
     set_cc_state_label,
 )
@@ -58,6 +60,7 @@ logger = logging.getLogger("k8s-cc-manager")
 CC_MODE_CONFIG_LABEL = "nvidia.com/cc.mode"
 READINESS_FILE = os.environ.get("CC_READINESS_FILE", "/run/nvidia/validations/.cc-manager-ctr-ready")
 VALID_MODES = ("on", "off", "devtools", "ppcie")
+SCRUB_SKIPPED_ANNOTATION = "nvidia.com/cc-manager.scrub-skipped"
 
 WATCH_TIMEOUT_SECONDS = 300
 RECONNECT_DELAY_SECONDS = 5
@@ -112,15 +115,28 @@ class CCManager:
         self.max_consecutive_errors = 10
 
         # --- new knobs (all optional; defaults keep the reference's behaviour + scrub)
+        # require: every GPU that went through a reset must pass the gate, a GPU that cannot be
+        #          scrubbed fails the transition (fail closed).
+        # auto:    GPUs WITHOUT a CUDA device behind them (vfio-bound for passthrough, or CC-on under
+        #          a bare-metal driver that cannot run CUDA) are released unscrubbed, loudly: warning
+        #          + node annotation; every GPU that can be scrubbed still must pass.
+        # skip:    no gate at all (the reference's behaviour).
         self.scrub_mode = (scrub_mode or env.get("CC_SCRUB_MODE", "require")).lower()
-        if self.scrub_mode not in ("require", "skip"):
-            raise ValueError(f"CC_SCRUB_MODE must be 'require' or 'skip', not {self.scrub_mode!r}")
+        if self.scrub_mode not in ("require", "auto", "skip"):
+            raise ValueError(f"CC_SCRUB_MODE must be 'require', 'auto' or 'skip', not {self.scrub_mode!r}")
+        if scrub_bytes is None and int(env.get("CC_SCRUB_BYTES", "0")) != 0 and self.scrub_mode != "skip" \
+                and env.get("CC_SCRUB_ALLOW_PARTIAL", "false").lower() != "true":
+            # a byte-limited scrub is a drill, not a gate: it leaves most of HBM unread
+            raise ValueError("CC_SCRUB_BYTES != 0 scrubs only part of HBM; set CC_SCRUB_ALLOW_PARTIAL=true "
+                             "to accept that (tests / drills), or leave it 0 for the full-HBM gate")
         self.scrub_bytes = int(scrub_bytes if scrub_bytes is not None else env.get("CC_SCRUB_BYTES", "0"))
         self.max_parallel = int(max_parallel if max_parallel is not None else env.get("CC_MAX_PARALLEL", "0"))
-        # "full-HBM" is enforced, not assumed: when scrubbing everything (scrub_bytes == 0) a GPU
-        # on which less than this fraction of device memory could be mapped fails the gate
-        # (something else still holds HBM, so part of it was NOT scrubbed).
-        self.scrub_min_coverage = float(env.get("CC_SCRUB_MIN_COVERAGE", "0.90"))
+        # "full-HBM" is enforced, not assumed: when scrubbing everything (scrub_bytes == 0) a GPU on
+        # which less than this fraction of DEVICE memory was zeroed and read back fails the gate
+        # (something else still holds HBM, so part of it was NOT scrubbed).  A clean B200 reaches
+        # 0.9966: all free HBM down to the last 2 MiB granule; the remainder is the CUDA context's
+        # own footprint (~0.6 GiB of 178.4 GiB), which no kernel of that context can map.
+        self.scrub_min_coverage = float(env.get("CC_SCRUB_MIN_COVERAGE", "0.99"))
         # A CUDA context must not outlive the gate: it pins HBM, blocks a vfio re-bind and would
         # not survive the next transition's device reset.  (Benchmarks that share the process
         # with other CUDA users switch this off.)
@@ -303,11 +319,42 @@ class CCManager:
             return True
         if self.mode_is_set(cc_gpus, mode):
             logger.info("All gpus already set to cc %s, skipping", mode)
+            if not self._regate_if_last_transition_failed(cc_gpus, mode):
+                return False
             set_cc_state_label(self.v1, self.node_name, mode)
             return True
         if self.evict_operator_components:
             return self._set_cc_mode_with_eviction(cc_gpus, mode)
         return self._set_cc_mode_direct(cc_gpus, mode)
+
+    def _regate_if_last_transition_failed(self, gpus: list, mode: str) -> bool:
+        """The registers already read `mode`, but the node still carries cc.mode.state=failed: the
+        last transition flipped the GPUs and then did NOT pass (e.g. the HBM scrub found dirt, or the
+        manager died before the verdict).  Publishing `mode` now would turn that failure into a
+        success without a single byte having been checked — so the gate runs first.
+        Only with a gate configured (require/auto); costs one node read on this path."""
+        if self.scrub_mode == "skip":
+            return True
+        try:
+            labels = self.v1.read_node(self.node_name).metadata.labels or {}
+        except ApiException as exc:
+            logger.warning("Could not read %s before publishing the state: %s", CC_MODE_STATE_LABEL, exc)
+            return True
+        if labels.get(CC_MODE_STATE_LABEL) != "failed":
+            return True
+        logger.warning("GPUs already read CC mode '%s' but the last transition FAILED: running the HBM scrub gate "
+                       "before the state is published", mode)
+        self.last_transition = {"mode": mode, "gpus": len(gpus), "phase_seconds": {}, "regate": True}
+        t0 = time.perf_counter()
+        try:
+            self._scrub_gate(gpus)
+        except Exception as exc:  # noqa: BLE001 - GpuError, ScrubFailure, anything: stay failed
+            logger.error("HBM scrub gate failed again: %s", exc)
+            self._finish_transition("failed", t0)
+            return False
+        self.last_transition["seconds_to_verdict"] = time.perf_counter() - t0
+        self._release_gate_resources()
+        return True
 
     def set_ppcie_mode(self) -> bool:
         """Protected-PCIe mode on every GPU and NVSwitch (reference main.py:265-296)."""
@@ -369,7 +416,11 @@ class CCManager:
 
     def _scrub_gate(self, reset_devices: list) -> None:
         """NEW stage: no GPU that went through a CC reset is
-        released before its HBM has been zero-filled and read back all-zero."""
+        released before its HBM has been zero-filled and read back all-zero.
+
+        Returns as soon as every verdict is in.  What the gate still holds then — HBM on its way
+        back to the driver (libccm's reaper) and the CUDA contexts — is given up by
+        _release_gate_resources(), which the callers run AFTER the state label is published."""
         gpus = [d for d in reset_devices if d.is_gpu()]
         if not gpus:
             return
@@ -377,17 +428,69 @@ class CCManager:
             logger.warning("CC_SCRUB_MODE=skip: releasing %d GPU(s) WITHOUT an HBM scrub", len(gpus))
             self.last_transition["scrub"] = "skipped"
             return
+        if self.scrub_mode == "auto":
+            blind = [g for g in gpus if not self._can_scrub(g)]
+            if blind:
+                names = ",".join(g.bdf for g in blind)
+                logger.warning("CC_SCRUB_MODE=auto: NO CUDA device behind %s (vfio-bound or CC-on under a driver "
+                               "that cannot run CUDA): releasing %d GPU(s) WITHOUT an HBM scrub", names, len(blind))
+                self.last_transition["scrub_skipped"] = [g.bdf for g in blind]
+                self._annotate({SCRUB_SKIPPED_ANNOTATION: names})
+                gpus = [g for g in gpus if self._can_scrub(g)]
+                if not gpus:
+                    self.last_transition["scrub"] = "skipped"
+                    return
+            else:
+                self._annotate({SCRUB_SKIPPED_ANNOTATION: None})
+        self._gate_gpus = list(gpus)
+        self._run_scrub(gpus)
+
+    @staticmethod
+    def _can_scrub(gpu) -> bool:
+        if isinstance(gpu, _devices.ScrubbingProxy):
+            return object.__getattribute__(gpu, "_native") is not None
+        if isinstance(gpu, _devices.NvidiaDevice):
+            return gpu.cuda_ordinal >= 0
+        return hasattr(gpu, "scrub_and_verify")
+
+    def _annotate(self, annotations: dict) -> None:
         try:
-            self._run_scrub(gpus)
-        finally:
-            if self.release_cuda_context:
-                for gpu in gpus:
-                    release = getattr(gpu, "release_cuda_context", None)
-                    if release is not None:
-                        try:
-                            release()
-                        except Exception as exc:  # noqa: BLE001 - never mask the gate's own verdict
-                            logger.warning("Could not release the CUDA context on %s: %s", gpu.bdf, exc)
+            self.v1.patch_node(self.node_name, {"metadata": {"annotations": annotations}})
+        except Exception as exc:  # noqa: BLE001 - informational only
+            logger.warning("Could not update node annotations %s: %s", sorted(annotations), exc)
+
+    def _release_gate_resources(self) -> None:
+        """Hands back what the scrub gate held: joins libccm's background HBM release and, with
+        CC_RELEASE_CUDA_CONTEXT=true (default), resets each GPU's CUDA primary context — all GPUs
+        at once (one native thread each).  Runs after the state label is out, so the driver's
+        unmap/release/teardown work overlaps the API round trips instead of delaying the verdict."""
+        gpus, self._gate_gpus = getattr(self, "_gate_gpus", []), []
+        if not gpus:
+            return
+        started = time.perf_counter()
+
+        def attempt(what, fn):
+            try:
+                fn()
+            except Exception as exc:  # noqa: BLE001 - never mask the gate's own verdict
+                logger.warning("Could not %s: %s", what, exc)
+
+        in_process = self.scrub_isolation != "process"   # a worker process took its contexts with it
+        native = [g for g in gpus if isinstance(g, _devices.NvidiaDevice)]
+        others = [g for g in gpus if not isinstance(g, _devices.NvidiaDevice)]
+        if self.release_cuda_context:
+            if native and in_process:
+                attempt("release the CUDA contexts", lambda: _devices.release_cuda_contexts(native))
+            for gpu in others:
+                release = getattr(gpu, "release_cuda_context", None)
+                if release is not None:
+                    attempt(f"release the CUDA context on {gpu.bdf}", release)
+        elif in_process:
+            for gpu in gpus:
+                wait = getattr(gpu, "wait_scrub_released", None)
+                if wait is not None:
+                    attempt(f"wait for the HBM release on {gpu.bdf}", wait)
+        self.last_transition.setdefault("phase_seconds", {})["release"] = time.perf_counter() - started
 
     def _scrub_in_worker_process(self, gpus: list) -> list:
         """CC_SCRUB_ISOLATION=process: one child runs the concurrent gate for all GPUs."""
@@ -433,10 +536,13 @@ class CCManager:
                     f"nonzero_bytes={rep.nonzero_bytes} of {rep.bytes_scrubbed}")
             if self.scrub_bytes == 0 and rep.coverage < self.scrub_min_coverage:
                 raise ScrubFailure(
-                    f"HBM scrub on {rep.bdf} covered only {100 * rep.coverage:.1f}% of device memory "
-                    f"(< {100 * self.scrub_min_coverage:.0f}%): another context still holds HBM")
-            logger.info("Scrubbed %s: %.1f GiB (%.1f%% of HBM) zeroed at %.0f GB/s, verified at %.0f GB/s, 0 non-zero bytes",
-                        rep.bdf, rep.bytes_scrubbed / 2**30, 100 * rep.coverage, rep.scrub_gbs, rep.verify_gbs)
+                    f"HBM scrub on {rep.bdf} covered only {100 * rep.coverage:.2f}% of device memory "
+                    f"(< {100 * self.scrub_min_coverage:.1f}%): {(rep.device_total_bytes - rep.bytes_scrubbed) >> 20} MiB "
+                    f"were not scrubbed ({rep.bytes_unreached >> 20} MiB free but unmappable, the rest held by other contexts)")
+            logger.info("Scrubbed %s: %.1f GiB (%.2f%% of HBM, %d MiB of free HBM unreached) zeroed at %.0f GB/s, "
+                        "verified at %.0f GB/s, 0 non-zero bytes",
+                        rep.bdf, rep.bytes_scrubbed / 2**30, 100 * rep.coverage, rep.bytes_unreached >> 20,
+                        rep.scrub_gbs, rep.verify_gbs)
         logger.info("HBM scrub gate passed on %d GPU(s) in %.3f s", len(reports), elapsed)
 
     def _set_cc_mode_direct(self, gpus: list, mode: str) -> bool:
@@ -457,17 +563,21 @@ class CCManager:
             self._scrub_gate(list(by_bdf.values()))
         except GpuError as exc:
             logger.error("GPU error setting CC mode: %s", exc)
-            set_cc_state_label(self.v1, self.node_name, "failed")
-            return False
+            return self._finish_transition("failed", t0)
         except Exception as exc:  # noqa: BLE001 - any failure marks the node failed
             logger.error("Unexpected error setting CC mode: %s", exc)
-            set_cc_state_label(self.v1, self.node_name, "failed")
-            return False
-        finally:
-            self.last_transition["seconds"] = time.perf_counter() - t0
+            return self._finish_transition("failed", t0)
         logger.info("Successfully set CC mode to '%s' on all GPUs", mode)
-        set_cc_state_label(self.v1, self.node_name, mode)
-        return True
+        return self._finish_transition(mode, t0)
+
+    def _finish_transition(self, state: str, t0: float) -> bool:
+        """Publishes the outcome (reference main.py:531-542), THEN gives the gate's GPU resources
+        back; `seconds_to_verdict` is what the label waited for, `seconds` the whole call."""
+        self.last_transition["seconds_to_verdict"] = time.perf_counter() - t0
+        set_cc_state_label(self.v1, self.node_name, state)
+        self._release_gate_resources()
+        self.last_transition["seconds"] = time.perf_counter() - t0
+        return state != "failed"
 
     def _set_ppcie_mode_direct(self, devices: list) -> bool:
         """reference main.py:317-391: PPCIe off where it is not (each device on its
@@ -495,17 +605,12 @@ class CCManager:
             self._scrub_gate(list(by_bdf.values()))
         except GpuError as exc:
             logger.error("GPU error setting PPCIe mode: %s", exc)
-            set_cc_state_label(self.v1, self.node_name, "failed")
-            return False
+            return self._finish_transition("failed", t0)
         except Exception as exc:  # noqa: BLE001
             logger.error("Unexpected error setting PPCIe mode: %s", exc)
-            set_cc_state_label(self.v1, self.node_name, "failed")
-            return False
-        finally:
-            self.last_transition["seconds"] = time.perf_counter() - t0
+            return self._finish_transition("failed", t0)
         logger.info("Successfully set PPCIe mode on all devices")
-        set_cc_state_label(self.v1, self.node_name, "ppcie")
-        return True
+        return self._finish_transition("ppcie", t0)
 
     def _with_eviction(self, what: str, transition: Callable[[], bool]) -> bool:
         """Pause operator components, run the transition, restore them — the
@@ -552,9 +657,30 @@ class CCManager:
         logger.info("Applying default CC mode: %s", self.default_mode)
         return self.default_mode
 
+    def recover_interrupted_transition(self) -> bool:
+        """SURVEY.md §8f N1.  The reference keeps the operator components' ORIGINAL deploy labels only
+        in memory between evict and reschedule (main.py:556-576): a manager that dies in between
+        leaves every component 'paused-for-cc-mode-change' for good.  With
+        CC_JOURNAL_COMPONENT_LABELS=true the originals are journaled in a node annotation before the
+        pause; a journal found at start-up means exactly that crash — the labels are restored (and
+        the journal cleared) before anything else, and the normal reconcile below then re-runs the
+        transition, re-evicting from the restored values.  Returns True if a journal was replayed."""
+        if not self.journal_labels:
+            return False
+        journaled = recover_journaled_labels(self.v1, self.node_name)
+        if journaled is None:
+            return False
+        logger.warning("Found the component-label journal of an INTERRUPTED transition on node %s: restoring %s",
+                       self.node_name, journaled)
+        if not reschedule_gpu_operator_components(self.v1, self.node_name, journaled, journal_annotation=True):
+            logger.error("Could not restore the journaled component labels; will retry on the next start")
+            return False
+        return True
+
     def watch_and_apply(self) -> None:
         """Apply the current label once, signal readiness, then follow the node's
         label forever (reference main.py:600-684)."""
+        self.recover_interrupted_transition()
         self.get_node_cc_mode_label()
         self.set_cc_mode(self.with_default(self.current_label))
         create_readiness_file()
@@ -613,16 +739,35 @@ class CCManager:
 
 
 def _device_source_from_env():
-    """CC_DEVICE_LIBRARY=gpu-admin-tools: keep NVIDIA/gpu-admin-tools for the register work (it is
-    looked up where the reference looks, <app dir>/gpu-admin-tools, reference main.py:30-31) and
-    add only the HBM scrub from libccm.so, matched by PCI address.  Default: libccm.so for both."""
-    choice = os.environ.get("CC_DEVICE_LIBRARY", "libccm").lower()
-    if choice in ("", "libccm"):
+    """Which library does the register work (query / stage / reset / wait_for_boot)?
+
+    CC_DEVICE_LIBRARY=gpu-admin-tools: NVIDIA/gpu-admin-tools, looked up where the reference looks
+        (<app dir>/gpu-admin-tools, reference main.py:30-31); libccm.so adds only the HBM scrub,
+        matched by PCI address.
+    CC_DEVICE_LIBRARY=libccm: libccm.so for both.
+    unset: gpu-admin-tools when that directory exists (the reference image ships it), else libccm.
+
+    The production entrypoint never drives a SIMULATED register file by accident (with no
+    env set, libccm picks its cudasim/sim backend and the manager would publish cc.mode.state=on
+    without having touched hardware): a simulated backend is refused unless CCM_ALLOW_SIM=1."""
+    tools = os.environ.get("GPU_ADMIN_TOOLS_PATH") or os.path.join(
+        os.path.dirname(os.path.abspath(sys.argv[0] or ".")), "gpu-admin-tools")
+    choice = os.environ.get("CC_DEVICE_LIBRARY", "").lower()
+    if not choice:
+        choice = "gpu-admin-tools" if os.path.isdir(tools) else "libccm"
+    if choice == "libccm":
+        from . import _native  # noqa: PLC0415
+        backend = _native.lib().ccm_backend_in_use()
+        if backend in (_native.BACKEND_SIM, _native.BACKEND_CUDASIM) \
+                and os.environ.get("CCM_ALLOW_SIM", "").lower() not in ("1", "true", "yes"):
+            name = {v: k for k, v in _native.BACKENDS.items()}[backend]
+            raise RuntimeError(
+                f"libccm selected its SIMULATED register backend ({name}): refusing to manage CC mode on "
+                "simulated registers.  Use CC_DEVICE_LIBRARY=gpu-admin-tools (real register access) or "
+                "CCM_BACKEND=sysfs, or set CCM_ALLOW_SIM=1 for drills and tests")
         return None
     if choice != "gpu-admin-tools":
         raise ValueError(f"CC_DEVICE_LIBRARY must be 'libccm' or 'gpu-admin-tools', not {choice!r}")
-    tools = os.environ.get("GPU_ADMIN_TOOLS_PATH") or os.path.join(
-        os.path.dirname(os.path.abspath(sys.argv[0] or ".")), "gpu-admin-tools")
     sys.path.insert(0, tools)
     from pci.devices import find_gpus as foreign_find_gpus  # noqa: PLC0415 - optional dependency
     return _devices.with_scrub(foreign_find_gpus)
@@ -639,7 +784,7 @@ def build_arg_parser() -> argparse.ArgumentParser:
     parser.add_argument("--node-name", default=env.get("NODE_NAME", ""),
                         help="Kubernetes node name (default: $NODE_NAME)")
     parser.add_argument("--debug", action="store_true", help="Enable debug logging")
-    parser.add_argument("--scrub-mode", default=None, choices=("require", "skip"),
+    parser.add_argument("--scrub-mode", default=None, choices=("require", "auto", "skip"),
                         help="HBM scrub gate after every CC transition (default: $CC_SCRUB_MODE or require)")
     return parser
 

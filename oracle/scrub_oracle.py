@@ -92,6 +92,10 @@ def clib() -> C.CDLL:
         lib.ccm_oracle_pattern_count.restype = C.c_uint64
         lib.ccm_oracle_scrub_verify_mt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
         lib.ccm_oracle_scrub_verify_mt.restype = C.c_uint64
+        lib.ccm_oracle_scrub_verify_mt_pinned.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        lib.ccm_oracle_scrub_verify_mt_pinned.restype = C.c_uint64
+        lib.ccm_oracle_fill_mt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        lib.ccm_oracle_fill_mt.restype = None
         _lib = lib
     return _lib
 
@@ -112,6 +116,29 @@ def pattern_count_c(nbytes: int, seed: int, word_index0: int = 0) -> int:
     return int(clib().ccm_oracle_pattern_count(nbytes, seed, word_index0))
 
 
-def scrub_verify_mt_c(buf: np.ndarray, threads: int, scrub: bool = True, verify: bool = True) -> int:
-    return int(clib().ccm_oracle_scrub_verify_mt(buf.ctypes.data, buf.nbytes, threads,
-                                                 (1 if scrub else 0) | (2 if verify else 0)))
+def scrub_verify_mt_c(buf: np.ndarray, threads: int, scrub: bool = True, verify: bool = True,
+                      pin: bool = False) -> int:
+    """memset + byte-wise count over `threads` contiguous slices.  pin=True: thread i runs on the
+    i-th allowed CPU (use with fill_mt_c so every slice is NUMA-local to its thread)."""
+    mode = (1 if scrub else 0) | (2 if verify else 0)
+    if pin:
+        return int(clib().ccm_oracle_scrub_verify_mt_pinned(buf.ctypes.data, buf.nbytes, threads, mode, 1))
+    return int(clib().ccm_oracle_scrub_verify_mt(buf.ctypes.data, buf.nbytes, threads, mode))
+
+
+def fill_mt_c(buf: np.ndarray, threads: int, byte: int, pin: bool = True) -> None:
+    """Parallel first touch: thread i fills slice i with `byte` (same partition / pinning as
+    scrub_verify_mt_c(pin=True))."""
+    clib().ccm_oracle_fill_mt(buf.ctypes.data, buf.nbytes, threads, byte & 0xFF, 1 if pin else 0)
+
+
+def numa_layout() -> str:
+    """'2 nodes: node0 cpus 0-63 ...' from sysfs, or 'unknown'."""
+    import glob
+    nodes = []
+    for path in sorted(glob.glob("/sys/devices/system/node/node[0-9]*")):
+        try:
+            nodes.append(f"{path.rsplit('/', 1)[1]} cpus {open(path + '/cpulist').read().strip()}")
+        except OSError:
+            pass
+    return f"{len(nodes)} NUMA node(s): " + "; ".join(nodes) if nodes else "NUMA layout unknown"

@@ -18,6 +18,8 @@ os.environ.setdefault("CC_READINESS_FILE", "/tmp/ccm-test-readiness/.cc-manager-
 # Inside ONE pytest process that context is shared with torch and with later tests, so the suite
 # keeps contexts alive; the release path is exercised in a subprocess (tests/test_context_release.py).
 os.environ.setdefault("CC_RELEASE_CUDA_CONTEXT", "false")
+# manager.main() refuses libccm's simulated register backends unless told the drill is intended
+os.environ.setdefault("CCM_ALLOW_SIM", "1")
 
 
 def pytest_configure(config):

@@ -1,5 +1,5 @@
 // Host-only stand-in for csrc/ccm_scrub.cu so that csrc/ccm_core.cpp (device table, register
-// backends, batched transition) can be built with plain g++ under -fsanitize=thread / address.
+// backends, concurrent launchers) can be built with plain g++ under -fsanitize=thread / address.
 // TEST INFRASTRUCTURE: every scrub entry point reports "no CUDA" exactly like a GPU-less box.
 #include "ccm_internal.h"
 
@@ -17,7 +17,8 @@ int engine_arena_step_times(ScrubEngine*, int, float*, float*, int*) { return CC
 int engine_arena_fill(ScrubEngine*, int, void*) { return CCM_ERR_NO_CUDA; }
 int engine_arena_fill_random(ScrubEngine*, uint64_t, void*) { return CCM_ERR_NO_CUDA; }
 int engine_arena_rw(ScrubEngine*, uint64_t, void*, uint64_t, bool) { return CCM_ERR_NO_CUDA; }
-int engine_scrub_verify(ScrubEngine*, uint64_t, ccm_scrub_result*) { return CCM_ERR_NO_CUDA; }
+int engine_scrub_verify(ScrubEngine*, uint64_t, uint64_t, ccm_scrub_result*) { return CCM_ERR_NO_CUDA; }
+int engine_release_wait(ScrubEngine*, double*, double*) { return CCM_ERR_NO_CUDA; }
 int engine_region_scrub(ScrubEngine*, void*, uint64_t, int, const ccm_launch_cfg*, void*, float*) { return CCM_ERR_NO_CUDA; }
 int engine_region_verify(ScrubEngine*, const void*, uint64_t, int, const ccm_launch_cfg*, void*, uint64_t*, float*) { return CCM_ERR_NO_CUDA; }
 int engine_host_roundtrip(ScrubEngine*, void*, uint64_t, uint64_t, int, int, uint64_t*, uint64_t*) { return CCM_ERR_NO_CUDA; }

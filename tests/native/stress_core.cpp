@@ -67,18 +67,30 @@ int main() {
       });
     for (auto& t : th) t.join();
   }
-  // 3. batched transitions on disjoint halves, concurrently, plus a faulty device
+  // 3. two full stage -> reset -> boot sequences on disjoint halves, concurrently, plus a faulty device
   {
     CHECK(ccm_sim_set(5, "fail_op", CCM_OP_WAIT_BOOT));
-    int a[8], b[8], sa[8], sb[8], ca[8], cb[8];
-    for (int i = 0; i < 8; ++i) { a[i] = i; b[i] = 8 + i; }
-    int rca = 0, rcb = 0;
-    std::thread ta([&] { rca = ccm_transition_many(8, a, CCM_CC_ON, 0, 1000, sa, ca); });
-    std::thread tb([&] { rcb = ccm_transition_many(8, b, CCM_CC_DEVTOOLS, 0, 1000, sb, cb); });
+    auto run_half = [](int first, int mode, int* status) {
+      std::vector<std::thread> th;
+      for (int i = 0; i < 8; ++i)
+        th.emplace_back([=] {
+          const int d = first + i;
+          int rc = ccm_set_cc_mode(d, mode);
+          if (rc == 0) rc = ccm_reset(d);
+          if (rc == 0) rc = ccm_wait_for_boot(d, 1000);
+          status[i] = rc;
+        });
+      for (auto& t : th) t.join();
+    };
+    int sa[8], sb[8];
+    std::thread ta([&] { run_half(0, CCM_CC_ON, sa); });
+    std::thread tb([&] { run_half(8, CCM_CC_DEVTOOLS, sb); });
     ta.join(); tb.join();
-    if (rca != CCM_ERR_FAULT || sa[5] != CCM_ERR_FAULT) { fprintf(stderr, "expected injected fault, got %d/%d\n", rca, sa[5]); failures++; }
-    if (rcb != 0) { fprintf(stderr, "second batch failed: %d\n", rcb); failures++; }
-    for (int i = 0; i < 8; ++i) { int m = -1; ccm_query_cc_mode(b[i], &m); if (m != CCM_CC_DEVTOOLS) failures++; }
+    if (sa[5] != CCM_ERR_FAULT) { fprintf(stderr, "expected injected fault, got %d\n", sa[5]); failures++; }
+    for (int i = 0; i < 8; ++i) {
+      if (sb[i] != 0) { fprintf(stderr, "second half failed: %d\n", sb[i]); failures++; }
+      int m = -1; ccm_query_cc_mode(8 + i, &m); if (m != CCM_CC_DEVTOOLS) failures++;
+    }
     // scrub on a device without CUDA must fail loudly, from many threads at once
     std::vector<std::thread> th;
     for (int d = 0; d < G; ++d)
@@ -87,6 +99,10 @@ int main() {
     ccm_scrub_result rs[16]; int all[16]; double wall = 0;
     for (int i = 0; i < G; ++i) all[i] = i;
     if (ccm_scrub_verify_many(G, all, 0, rs, &wall) != CCM_ERR_NO_CUDA) failures++;
+    // nothing is pending / held on a device without CUDA: the waits and releases are cheap no-ops
+    double rel = -1, waited = -1;
+    if (ccm_scrub_release_wait(0, &rel, &waited) != CCM_ERR_NO_CUDA || rel != 0 || waited != 0) failures++;
+    CHECK(ccm_device_release_many(G, all, &wall));
   }
   printf("stress_core: %d failures\n", failures.load());
   return failures ? 1 : 0;

@@ -22,7 +22,8 @@ def test_header_declares_the_documented_surface():
     names = declared_functions()
     assert len(names) >= 30
     for must in ("ccm_enumerate", "ccm_query_cc_mode", "ccm_set_cc_mode", "ccm_reset", "ccm_wait_for_boot",
-                 "ccm_scrub_verify", "ccm_scrub_verify_many", "ccm_transition_many", "ccm_strerror"):
+                 "ccm_scrub_verify", "ccm_scrub_verify_many", "ccm_scrub_release_wait", "ccm_device_release_many",
+                 "ccm_strerror"):
         assert must in names
 
 
@@ -35,13 +36,13 @@ def test_library_exports_every_declared_symbol(native):
     assert declared <= exported, declared - exported
     assert exported <= declared, f"exported but undeclared: {exported - declared}"
     assert set(native.EXPORTED_SYMBOLS) == declared
-    assert lib.ccm_abi_version() == 1
+    assert lib.ccm_abi_version() == native.ABI_VERSION == 2
 
 
 def test_every_entry_point_cites_the_reference_or_says_new():
     """include/ccm.h must tie each device op to the reference call site it replaces."""
     for fn in ("ccm_query_cc_mode", "ccm_set_cc_mode", "ccm_query_ppcie_mode", "ccm_set_ppcie_mode", "ccm_reset",
-               "ccm_wait_for_boot", "ccm_enumerate", "ccm_transition_many"):
+               "ccm_wait_for_boot", "ccm_enumerate"):
         idx = re.search(rf"^int {fn}\(", HEADER, re.M).start()
         assert "main.py:" in HEADER[max(0, idx - 700):idx], fn
 
@@ -49,15 +50,17 @@ def test_every_entry_point_cites_the_reference_or_says_new():
 def test_struct_layouts_match_header(native, tmp_path):
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ccm.h"\nint main(void){'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ccm_dev_info), sizeof(ccm_launch_cfg),'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ccm_dev_info), sizeof(ccm_launch_cfg),'
                    'sizeof(ccm_scrub_result), sizeof(ccm_arena_info), offsetof(ccm_dev_info,bdf),'
-                   'offsetof(ccm_scrub_result,ms_acquire), offsetof(ccm_scrub_result,status));return 0;}')
+                   'offsetof(ccm_scrub_result,ms_acquire), offsetof(ccm_scrub_result,status),'
+                   'offsetof(ccm_scrub_result,device_free_before), offsetof(ccm_scrub_result,ms_gpu_span));return 0;}')
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     N = native
     assert got == [C.sizeof(N.DevInfo), C.sizeof(N.LaunchCfg), C.sizeof(N.ScrubResult), C.sizeof(N.ArenaInfo),
-                   N.DevInfo.bdf.offset, N.ScrubResult.ms_acquire.offset, N.ScrubResult.status.offset]
+                   N.DevInfo.bdf.offset, N.ScrubResult.ms_acquire.offset, N.ScrubResult.status.offset,
+                   N.ScrubResult.device_free_before.offset, N.ScrubResult.ms_gpu_span.offset]
 
 
 def test_header_is_plain_c(tmp_path):

@@ -103,49 +103,6 @@ def test_boot_timeout(sim):
     assert g.query_cc_mode() == "off"
 
 
-def test_transition_many_is_concurrent_and_ordered(sim):
-    """8 GPUs x (100 ms reset + 150 ms boot): serial would need >= 2 s; the batched
-    call joins per phase, so ~ one reset + one boot."""
-    sim_set(-1, "reset_ms", 100)
-    sim_set(-1, "boot_ms", 150)
-    n = 8
-    devs = (C.c_int * n)(*range(n))
-    st, ch = (C.c_int * n)(), (C.c_int * n)()
-    t0 = time.perf_counter()
-    rc = N.lib().ccm_transition_many(n, devs, N.CC_MODES["on"], 0, 0, st, ch)
-    dt = time.perf_counter() - t0
-    assert rc == 0 and list(st) == [0] * n and list(ch) == [1] * n
-    assert dt < 1.0, f"batched transition took {dt:.2f}s: phases are not concurrent"
-    assert dt >= 0.24
-    ops = [l.split()[1] for l in sim_trace()]
-    assert max(i for i, o in enumerate(ops) if o == "set_cc_mode") < min(i for i, o in enumerate(ops) if o == "reset_with_os")
-    assert max(i for i, o in enumerate(ops) if o == "reset_with_os") < min(i for i, o in enumerate(ops) if o == "wait_for_boot")
-    assert all(sim_get(i, "cc_mode") == 1 for i in range(n))
-    # idempotent: nothing changes the second time
-    rc = N.lib().ccm_transition_many(n, devs, N.CC_MODES["on"], 0, 0, st, ch)
-    assert rc == 0 and list(ch) == [0] * n
-
-
-def test_transition_many_staging_error_resets_nothing(sim):
-    from helpers import OP_BITS
-    sim_set(3, "fail_op", OP_BITS["set_cc_mode"])
-    n = 8
-    devs = (C.c_int * n)(*range(n))
-    st, ch = (C.c_int * n)(), (C.c_int * n)()
-    rc = N.lib().ccm_transition_many(n, devs, 1, 0, 0, st, ch)
-    assert rc == N.ERR_FAULT and st[3] == N.ERR_FAULT
-    assert not any("reset_with_os" in l for l in sim_trace())
-    assert all(sim_get(i, "cc_mode") == 0 for i in range(n))
-
-
-def test_transition_many_ppcie_includes_switches(sim):
-    n = 12
-    devs = (C.c_int * n)(*range(n))
-    st, ch = (C.c_int * n)(), (C.c_int * n)()
-    assert N.lib().ccm_transition_many(n, devs, 1, 1, 0, st, ch) == 0
-    assert all(sim_get(i, "ppcie_mode") == 1 for i in range(n))
-
-
 def test_python_manager_wallclock_scales_with_max_not_sum(sim, monkeypatch):
     """The concurrent launcher: per-GPU reset/boot latencies overlap."""
     import kubernetes
