@@ -3,25 +3,40 @@
 
 Contract (driver):  python bench.py --gpus N --steps K --warmup W      [--impl reference]
   N>1 is launched by the driver as torchrun with one rank per GPU (NCCL is used ONLY
-  for the barrier and the max/sum of the timings: the path is per-GPU independent, no
-  data-path collective — SURVEY.md §8e).
+  for the barrier and the max/sum/gather of the timings: the path is per-GPU independent,
+  no data-path collective — SURVEY.md §8e).
 
 A "step" = one pass of the hot path over one region: the scrub kernel zero-fills
 every byte of the arena, then the verify kernel reads it back and counts non-zero
 bytes.  Workload = BASELINE.json configs[1]: one B200, all the HBM a CUDA context can
-map (~190.6 GB of 191.5 GB), poisoned with 0xA5 before the first step.
+map (~190.8 GB of 191.5 GB), poisoned with 0xA5 before the first step.
 
-  value   whole-job GB/s with the region resident in HBM: (bytes zeroed + bytes read
-          back) over all ranks / max-over-ranks CUDA-event time of the K steps.
-  e2e     the same metric through the public API a manager calls
-          (k8s_cc_manager_b200.devices.Gpu.scrub_and_verify): cold call that acquires
-          the arena (cudaMalloc of all free HBM), runs both kernels, reads the 8-byte
-          count back to the host and frees the arena.  The path has NO host-resident
-          input — it takes a device index — so h2d_bytes_per_step is 0 and
-          d2h_bytes_per_step is the 8-byte count.
-  roofline     scrub kernel (HBM write bound): R bytes / mean CUDA-event duration of the
-               scrub launches inside the timed region, vs MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline the oracle's C port (memset + byte-wise count) on the box's host cores.
+  value     whole-job GB/s with the region resident in HBM: (bytes zeroed + bytes read
+            back) over all ranks / max-over-ranks CUDA-event time of the K steps.
+  e2e       the same metric through the public API a manager calls
+            (k8s_cc_manager_b200.devices.Gpu.scrub_and_verify -> ccm_scrub_verify): a COLD
+            call maps all free HBM, scrubs and reads back chunk by chunk, copies the 8-byte
+            count to the host and hands the HBM back.  >= 15 calls; every call starts on a
+            barrier over the ranks.  `value` counts the WHOLE cycle (call -> HBM back with
+            the driver); `verdict_s` is the part a transition waits for (the release runs on
+            libccm's reaper thread, off the critical path).  Median / p10 / p90 over calls of
+            the max over ranks.  No host-resident input exists on this path (it takes a device
+            index): h2d_bytes_per_step = 0, d2h_bytes_per_step = 8.
+  roofline  scrub kernel (HBM write bound): R bytes / mean CUDA-event duration of the scrub
+            launches inside the timed region, vs MEASURED_PEAKS.json hbm_gbs; plus the
+            library write bar (cudaMemsetAsync) and a library read-only pass (torch sum)
+            timed in the SAME run.
+  checks    hardware proof at every N: k = 7 bytes injected at seeded offsets (first, last,
+            unaligned) are counted exactly, on every rank; after the ranks are done, ONE process
+            drives all N GPUs through the concurrent launcher (clean + coverage + a dirt drill).
+  transition  BASELINE metric 1 at every N: CCManager.set_cc_mode off->on->devtools->off,
+            eviction-gated, on the first N GPUs from one process — once with the daemon's
+            defaults (CUDA contexts released after every gate) and once with contexts kept;
+            constructed baselines B1/B2 in the same run.
+  cpu_baseline  the oracle's C port (memset + byte-wise count) on the box's host cores,
+            NUMA-local first touch, pinned threads.
+
+Other modes:  --sweep  region sweep 1 GB -> max (BASELINE configs[4]) on this rank's GPU.
 """
 from __future__ import annotations
 
@@ -30,6 +45,7 @@ import ctypes as C
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -41,6 +57,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "HBM scrub-and-verify throughput (bytes zeroed + bytes read back per second, whole job)"
 UNIT = "GB/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+DATASHEET_HBM_GBS = 8000.0  # HBM3e nominal, B200
 
 
 def measured_peak():
@@ -51,6 +68,16 @@ def measured_peak():
         except Exception:  # noqa: BLE001
             pass
     return FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, max(0, round(q * (len(xs) - 1))))] if xs else float("nan")
+
+
+def stats(xs):
+    return {"median": statistics.median(xs), "p10": pct(xs, 0.1), "p90": pct(xs, 0.9), "min": min(xs), "max": max(xs),
+            "n": len(xs)}
 
 
 # ------------------------------------------------------------------ clock sampler
@@ -107,31 +134,39 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------- CPU baseline
-def cpu_scrub_verify(sample_gib: float, budget_s: float, passes_max: int = 64):
-    """oracle/scrub_oracle.c (memset + byte-wise non-zero count) on the host cores.
-    This is the ONLY place bench.py executes oracle code, and only as the baseline."""
+def host_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_arm(sample_gib: float, passes: int, warm: int):
+    """oracle/scrub_oracle.c (memset + byte-wise non-zero count) on the host cores — the ONLY place
+    bench.py executes oracle code, and only as the baseline.  Thread i is pinned to the i-th allowed
+    CPU and first-touches its own slice, so every slice lives on the NUMA node that streams it
+    (round 1 first-touched from one thread: 26 GB/s on one box, 112 GB/s on another)."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import numpy as np
     import scrub_oracle as SO
 
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = host_threads()
     nbytes = int(sample_gib * 2**30)
     buf = np.empty(nbytes, dtype=np.uint8)
-    buf[:] = 0xA5                                      # first touch + poison (untimed)
-    assert SO.scrub_verify_mt_c(buf, threads, scrub=False) == nbytes
-    assert SO.scrub_verify_mt_c(buf, threads) == 0     # warm pass (untimed)
-    passes, t0 = 0, time.perf_counter()
-    while passes < passes_max:
-        nz = SO.scrub_verify_mt_c(buf, threads)
-        passes += 1
+    SO.fill_mt_c(buf, threads, 0xA5, pin=True)                       # parallel first touch + poison (untimed)
+    assert SO.scrub_verify_mt_c(buf, threads, scrub=False, pin=True) == nbytes
+    for _ in range(max(1, warm)):
+        assert SO.scrub_verify_mt_c(buf, threads, pin=True) == 0      # warm passes (untimed)
+    times = []
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        nz = SO.scrub_verify_mt_c(buf, threads, pin=True)
+        times.append(time.perf_counter() - t0)
         assert nz == 0
-        if time.perf_counter() - t0 >= budget_s:
-            break
-    dt = time.perf_counter() - t0
-    return {"value": 2.0 * nbytes * passes / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{sample_gib:g} GiB host buffer x {passes} passes of memset + byte-wise count "
-                      f"on {threads} pthreads (oracle/scrub_oracle.c); the reference has no scrub to time",
-            "seconds": dt, "bytes_per_pass": nbytes, "passes": passes}
+    rates = [2.0 * nbytes / t / 1e9 for t in times]
+    sample = (f"{sample_gib:g} GiB host buffer, {passes} timed passes of memset + byte-wise count on {threads} pinned "
+              f"pthreads, each first-touching and then streaming its own slice (oracle/scrub_oracle.c; the reference has "
+              f"no scrub to time); {SO.numa_layout()}")
+    return {"value": 2.0 * nbytes * passes / sum(times) / 1e9, "best": max(rates), "median": statistics.median(rates),
+            "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": sum(times),
+            "bytes_per_pass": nbytes, "passes": passes}
 
 
 def run_reference_arm(args):
@@ -141,28 +176,16 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import numpy as np
-    import scrub_oracle as SO
-
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    nbytes = int(args.cpu_sample_gib * 2**30)
-    buf = np.empty(nbytes, dtype=np.uint8)
-    buf[:] = 0xA5
-    for _ in range(max(1, args.warmup)):
-        SO.scrub_verify_mt_c(buf, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        assert SO.scrub_verify_mt_c(buf, threads) == 0
-    dt = time.perf_counter() - t0
-    value = 2.0 * nbytes * args.steps / dt / 1e9
-    sample = (f"each step = memset + byte-wise count over a {args.cpu_sample_gib:g} GiB host buffer on "
-              f"{threads} pthreads (bounded sample of the {args.gpus}-GPU workload)")
+    cb = cpu_arm(args.cpu_sample_gib, passes=args.steps, warm=max(1, args.warmup))
+    value = cb["value"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds"] / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1] CPU statement: scrub + read-back verify of a host buffer", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": "configs[1] CPU statement: scrub + read-back verify of a host buffer",
+                       "sample": cb["sample"], "same_config": False,
+                       "note": f"bounded sample: {args.cpu_sample_gib:g} GiB per step instead of the GPU arm's ~190.8 GB per GPU "
+                               "(a bandwidth-bound loop: GB/s does not depend on the length)"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "best", "median", "unit", "cores", "kind", "sample")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -175,12 +198,34 @@ def check(rc, what):
         raise RuntimeError(f"{what}: {N.strerror(rc)}: {N.last_error()}")
 
 
+def injected_count_check(L, N, dev, R, vv, sptr):
+    """k = 7 bytes at seeded offsets — first byte, last byte, one non-16-aligned offset, four random
+    ones — must be counted exactly; after a scrub the count is 0 again (tests/test_scrub_gpu.py
+    :134-163 at full size, on every rank)."""
+    import numpy as np
+    rng = np.random.default_rng(1234 + dev)
+    offs = {0, R - 1, 16 * 1000 + 3}
+    while len(offs) < 7:
+        offs.add(int(rng.integers(0, R)))
+    nz = C.c_uint64()
+    for o in sorted(offs):
+        check(L.ccm_arena_write(dev, o, (C.c_uint8 * 1)(int(rng.integers(1, 256))), 1), "arena_write")
+    check(L.ccm_arena_verify(dev, vv, None, sptr, C.byref(nz), None), "verify injected")
+    found = nz.value
+    check(L.ccm_arena_scrub(dev, N.SCRUB_AUTO, None, sptr, None), "scrub")
+    check(L.ccm_arena_verify(dev, vv, None, sptr, C.byref(nz), None), "verify after scrub")
+    ok = found == 7 and nz.value == 0
+    if not ok:
+        raise RuntimeError(f"injected 7 bytes, verify counted {found}; after scrub {nz.value}")
+    return {"injected": 7, "counted": found, "after_scrub": nz.value, "offsets_include": ["first byte", "last byte", "unaligned"]}
+
+
 def run_ours(args):
     import torch
 
     from k8s_cc_manager_b200 import _native as N
     from k8s_cc_manager_b200 import devices as D
-    from k8s_cc_manager_b200.aggregate import aggregate_job
+    from k8s_cc_manager_b200.aggregate import aggregate_cold_calls, aggregate_job, gather_rows as gather_rows_
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,12 +251,16 @@ def run_ours(args):
         dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
         return float(t.item())
 
+    def gather_rows(rows):
+        return gather_rows_(dist, "cuda", rows)
+
     if dist:
         # NCCL allocates its communicator buffers lazily: touch every collective used below
         # BEFORE the arena takes all free HBM, and leave it headroom.
         barrier()
         reduce(0.0, "MAX")
         reduce(0.0, "SUM")
+        gather_rows([[0.0, 0.0]])
         os.environ.setdefault("CCM_ARENA_RESERVE_MB", "1024")
 
     L = N.lib()
@@ -219,6 +268,7 @@ def run_ours(args):
     dev = local
     sv = N.SCRUB_VARIANTS[args.scrub]
     vv = N.VERIFY_VARIANTS[args.verify]
+    k_scrub, k_verify = N.default_kernels()
 
     # ---- resident region: everything the context can map (or --gib) -------------------
     ai = N.ArenaInfo()
@@ -236,6 +286,10 @@ def run_ours(args):
     check(L.ccm_arena_verify(dev, vv, None, sptr, C.byref(nz), None), "verify poison")
     if nz.value != R:
         raise RuntimeError(f"poisoned arena must read back {R} non-zero bytes, got {nz.value}")
+    checks = {"poison_counted": nz.value == R}
+    check(L.ccm_arena_scrub(dev, sv, None, sptr, None), "scrub")
+    checks["injection"] = injected_count_check(L, N, dev, R, vv, sptr)
+    check(L.ccm_arena_fill(dev, 0xA5, sptr), "re-poison")       # the timed steps start from dirty memory
 
     def step():
         check(L.ccm_arena_scrub_verify_async(dev, sv, vv, None, None, sptr), "scrub_verify_async")
@@ -267,25 +321,68 @@ def run_ours(args):
     check(L.ccm_arena_step_times(dev, 64, s_ms, v_ms, C.byref(nsteps)), "step_times")
     scrub_ms = statistics.mean(s_ms[:nsteps.value]) if nsteps.value else float("nan")
     verify_ms = statistics.mean(v_ms[:nsteps.value]) if nsteps.value else float("nan")
+
+    # ---- same-run peaks: the library write bar over the same arena ... ------------------
+    peaks = {}
+    ms = C.c_float()
+    best = 1e30
+    for _ in range(4):
+        check(L.ccm_arena_scrub(dev, N.SCRUB_MEMSET, None, sptr, C.byref(ms)), "memset pass")
+        best = min(best, ms.value)
+    peaks["peak_write_same_run"] = R / best / 1e6
+    peaks["peak_write_how"] = "cudaMemsetAsync over the same arena, best of 4 (CUDA events)"
     check(L.ccm_arena_release(dev), "arena_release")
+    # ... and a library read-only pass (torch reduction over 32 GiB, >> L2)
+    try:
+        n_read = min(32 << 30, R // 2) // 8
+        t = torch.zeros(n_read, dtype=torch.int64, device="cuda")
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(4):
+            a.record(stream)
+            t.sum()
+            b.record(stream)
+            b.synchronize()
+            best = min(best, a.elapsed_time(b))
+        peaks["peak_read_same_run"] = n_read * 8 / best / 1e6
+        peaks["peak_read_how"] = f"torch.sum over {n_read * 8 >> 30} GiB of int64 (library reduction kernel), best of 4"
+        del t
+    except Exception as exc:  # noqa: BLE001
+        peaks["peak_read_error"] = str(exc)
+    torch.cuda.empty_cache()
 
     agg = aggregate_job(dist, "cuda", region_bytes=R, steps=args.steps, elapsed_ms=ms_local, launches=launches)
-    ms, value, total_launches = agg["ms"], agg["value_gbs"], agg["launches"]
+    ms_total, value, total_launches = agg["ms"], agg["value_gbs"], agg["launches"]
 
-    # ---- e2e: the public API, cold (acquire + kernels + D2H count + release) -----------
+    # ---- e2e: the public API, cold; every call starts on a barrier over the ranks -------
     gpu = [d for d in D.find_gpus()[0] if d.is_gpu()][dev]
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    want = int(args.gib * 2**30) if args.gib > 0 else 0
+    e2e_steps = max(1, args.e2e_steps)
     for _ in range(max(3, args.warmup)):                                     # same W as the kernel arm
-        gpu.scrub_and_verify(int(args.gib * 2**30) if args.gib > 0 else 0)
+        gpu.scrub_and_verify(want)
+    gpu.wait_scrub_released()
+    rows, reports = [], []
     barrier()
-    t0 = time.perf_counter()
-    reports = [gpu.scrub_and_verify(int(args.gib * 2**30) if args.gib > 0 else 0) for _ in range(e2e_steps)]
-    torch.cuda.synchronize()
-    e2e_local = time.perf_counter() - t0
+    t_loop = time.perf_counter()
+    for _ in range(e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        rep = gpu.scrub_and_verify(want)                # returns with the verdict (8-byte count on the host)
+        t1 = time.perf_counter()
+        ms_rel, _waited = gpu.wait_scrub_released()     # HBM back with the driver
+        t2 = time.perf_counter()
+        reports.append(rep)
+        rows.append([t1 - t0, t2 - t0, float(rep.bytes_scrubbed), rep.ms_acquire, rep.ms_gpu_span, rep.ms_scrub,
+                     rep.ms_verify, ms_rel])
     barrier()
-    e2e_s = reduce(e2e_local, "MAX")
-    e2e_bytes = reduce(float(sum(r.bytes_scrubbed for r in reports)), "SUM")
-    e2e_value = 2.0 * e2e_bytes / e2e_s / 1e9
+    loop_s = reduce(time.perf_counter() - t_loop, "MAX")
+    all_rows = gather_rows(rows)                        # [rank][call][col]
+    cold = aggregate_cold_calls(all_rows)
+    verdict, cycle, e2e_value = cold["verdict_s_each"], cold["cycle_s_each"], cold["value_gbs"]
+    phase_names = ["acquire_host_ms", "gpu_span_ms", "scrub_kernels_ms", "verify_kernels_ms", "release_ms"]
+    phases = {name: {"median_of_max_over_ranks": statistics.median(
+        max(all_rows[r][i][3 + j] for r in range(world)) for i in range(e2e_steps))}
+        for j, name in enumerate(phase_names)}
     last = reports[-1]
 
     # ---- informational: the same kernels driven with a HOST buffer (ccm_host_roundtrip:
@@ -312,26 +409,33 @@ def run_ours(args):
                    "d2h_bytes_per_step": hb + 16, "steps": len(times), "seconds_per_step": sum(times) / len(times),
                    "api": "ccm_host_roundtrip (C ABI): pinned host buffer -> device -> count, scrub, count -> host",
                    "note": "PCIe-bound; informational — the manager's call takes no host buffer"}
+        del pinned
 
-    # ---- node transition through the manager (N=1 only; registers + API simulated) ----
-    transition = None
-    if world == 1 and not args.no_transition:
-        transition = measure_transition(L, N)
+    all_checks = gather_rows([[1.0 if checks["poison_counted"] else 0.0, float(checks["injection"]["counted"]),
+                               float(checks["injection"]["after_scrub"])]])
+    if dist:
+        dist.destroy_process_group()
+    if rank != 0:
+        return                                            # the node leg needs the other GPUs idle
 
     peak, peak_src = measured_peak()
-    # DRAM traffic per launch: from the committed ncu capture (never measured under this run),
-    # scaled to this run's region size.
+    # DRAM traffic per launch: from the committed ncu capture (never measured under this run), scaled to
+    # this run's region size — and only if the capture is of the kernels this library launches today.
     traffic_s = traffic_v = None
+    traffic_src = "profiles/traffic.json (ncu dram__bytes_read+write of one full-arena launch)"
     try:
         tr = json.loads((ROOT / "profiles" / "traffic.json").read_text())
         k = R / tr["region_bytes"]
-        traffic_s = int(k * (tr["scrub_st_kernel"]["dram_bytes_read"] + tr["scrub_st_kernel"]["dram_bytes_write"]))
-        traffic_v = int(k * (tr["verify_ld_kernel"]["dram_bytes_read"] + tr["verify_ld_kernel"]["dram_bytes_write"]))
+        traffic_s = int(k * (tr["kernels"][k_scrub]["dram_bytes_read"] + tr["kernels"][k_scrub]["dram_bytes_write"]))
+        traffic_v = int(k * (tr["kernels"][k_verify]["dram_bytes_read"] + tr["kernels"][k_verify]["dram_bytes_write"]))
+    except KeyError:
+        traffic_src = "profiles/traffic.json is STALE: it does not hold the kernels libccm launches now"
     except Exception:  # noqa: BLE001
-        pass
+        traffic_src = "profiles/traffic.json unreadable"
+    scrub_gbs, verify_gbs = R / scrub_ms / 1e6, R / verify_ms / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {
             "workload": "BASELINE configs[1]: B200 off->on transition scrub over all mappable HBM, "
@@ -341,77 +445,382 @@ def run_ours(args):
             "l2": "no flush needed: region (>=190 GB) is >1000x the 126 MB L2; every step re-streams it",
             "parallelism": f"{world} independent GPU(s), one process per GPU, no data-path collective",
         },
-        "per_gpu": {"scrub_gbs": R / scrub_ms / 1e6, "verify_gbs": R / verify_ms / 1e6,
-                    "scrub_ms": scrub_ms, "verify_ms": verify_ms, "step_gbs": 2.0 * R * args.steps / ms_local / 1e6},
-        "roofline": {"bound": "hbm", "kernel": "scrub_st256_fast_kernel<512,8> (HBM write)", "achieved": R / scrub_ms / 1e6,
-                     "peak": peak, "unit": "GB/s", "frac": R / scrub_ms / 1e6 / peak, "traffic": traffic_s,
-                     "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write of one full-arena launch)",
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": R, "note": "of measured" if "MEASURED" in peak_src else "of fallback"},
-        "roofline_verify": {"bound": "hbm", "kernel": "verify_ld256_fast_kernel<1024,4> (HBM read)", "achieved": R / verify_ms / 1e6,
-                            "peak": peak, "unit": "GB/s", "frac": R / verify_ms / 1e6 / peak, "traffic": traffic_v,
-                            "algorithmic_bytes_per_launch": R},
+        "per_gpu": {"scrub_gbs": scrub_gbs, "verify_gbs": verify_gbs, "scrub_ms": scrub_ms, "verify_ms": verify_ms,
+                    "step_gbs": 2.0 * R * args.steps / ms_local / 1e6},
+        "roofline": {"bound": "hbm", "kernel": f"{k_scrub} (HBM write)", "achieved": scrub_gbs,
+                     "peak": peak, "unit": "GB/s", "frac": scrub_gbs / peak, "traffic": traffic_s,
+                     "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": R, "note": "of measured" if "MEASURED" in peak_src else "of fallback",
+                     **peaks,
+                     "frac_vs_write_peak": scrub_gbs / peaks["peak_write_same_run"],
+                     "frac_vs_datasheet": scrub_gbs / DATASHEET_HBM_GBS},
+        "roofline_verify": {"bound": "hbm", "kernel": f"{k_verify} (HBM read)", "achieved": verify_gbs,
+                            "peak": peak, "unit": "GB/s", "frac": verify_gbs / peak, "traffic": traffic_v,
+                            "algorithmic_bytes_per_launch": R,
+                            "frac_vs_read_peak": verify_gbs / peaks["peak_read_same_run"] if "peak_read_same_run" in peaks else None,
+                            "frac_vs_datasheet": verify_gbs / DATASHEET_HBM_GBS},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
-                "steps": e2e_steps, "warmup": max(3, args.warmup), "seconds_per_step": e2e_s / e2e_steps,
-                "ms_total_each_step": [r.ms_total for r in reports],
-                "breakdown_ms_last_step": {"acquire": last.ms_acquire, "scrub": last.ms_scrub,
-                                           "verify": last.ms_verify, "release": last.ms_release,
-                                           "total": last.ms_total},
-                "api": "k8s_cc_manager_b200.devices.Gpu.scrub_and_verify -> ccm_scrub_verify (C ABI)",
-                "note": "no host-resident input exists on this path; timed region covers arena acquire, "
-                        "both kernels, D2H of the 8-byte count, arena release"},
+                "steps": e2e_steps, "warmup": max(3, args.warmup),
+                "seconds_per_step": statistics.median(cycle),
+                "cycle_s": cold["cycle_s"], "verdict_s": cold["verdict_s"],
+                "verdict_value": cold["verdict_value_gbs"],
+                "loop_wall_s": loop_s,
+                "phases": phases,
+                "ms_verdict_each_step": [round(x * 1e3, 2) for x in verdict],
+                "ms_cycle_each_step": [round(x * 1e3, 2) for x in cycle],
+                "breakdown_ms_last_step_rank0": {"acquire_host": last.ms_acquire, "gpu_span": last.ms_gpu_span,
+                                                 "scrub_kernels": last.ms_scrub, "verify_kernels": last.ms_verify,
+                                                 "to_verdict": last.ms_total, "chunks": last.segments,
+                                                 "bytes_unreached": last.bytes_unreached, "coverage": last.coverage},
+                "api": "k8s_cc_manager_b200.devices.Gpu.scrub_and_verify -> ccm_scrub_verify (C ABI); "
+                       "Gpu.wait_scrub_released -> ccm_scrub_release_wait",
+                "note": "value = 2 x bytes / sum over calls of the max-over-ranks CYCLE time (call start -> verdict -> "
+                        "HBM handed back); every call starts on a barrier.  verdict_s is what a transition waits "
+                        "for: the unmap/release runs on libccm's reaper thread.  Back-to-back cold calls are the "
+                        "driver's worst case (it re-allocates memory it is still scrubbing after the last free).  "
+                        "No host-resident input exists on this path."},
         "gpu_launches": total_launches,
         "clocks": clocks,
+        "checks": {"per_rank": {"poison_counted": [bool(r[0][0]) for r in all_checks],
+                                "injected_7_counted": [int(r[0][1]) for r in all_checks],
+                                "after_scrub": [int(r[0][2]) for r in all_checks]},
+                   "ok": all(r[0][0] == 1.0 and r[0][1] == 7.0 and r[0][2] == 0.0 for r in all_checks)},
     }
     if host_rt:
         line["e2e_host_buffers"] = host_rt
-    if transition:
-        line["transition"] = transition
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_scrub_verify(args.cpu_sample_gib, args.cpu_budget_s)
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if dist:
-        dist.destroy_process_group()
+    if not args.no_node_leg:
+        node = run_node_leg(world, args)
+        for key in ("node_checks", "transition", "baselines"):
+            if key in node:
+                if key == "node_checks":
+                    line["checks"]["node"] = node[key]
+                    line["checks"]["ok"] = bool(line["checks"]["ok"] and node[key].get("ok"))
+                else:
+                    line[key] = node[key]
+        if "error" in node:
+            line["node_leg_error"] = node["error"]
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_arm(args.cpu_sample_gib, passes=args.cpu_passes, warm=2)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
 
 
-def measure_transition(L, N):
-    """BASELINE metric 1 on ONE GPU: wall-clock of CCManager.set_cc_mode('on') from 'off',
-    eviction-gated.  Simulated and reported as such: CC registers, reset/boot latency
-    (0 ms), the k8s API server (in-memory).  Real: the full-HBM scrub gate."""
+# ------------------------------------------------------------------------ node leg
+def wait_for_idle_gpus(n, timeout_s=60.0):
+    """The other ranks exit after the per-rank phases; wait until their processes are gone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        me = os.getpid()
+        deadline = time.time() + timeout_s
+        while time.time() < deadline:
+            busy = 0
+            for i in range(n):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                busy += sum(1 for p in pynvml.nvmlDeviceGetComputeRunningProcesses(h) if p.pid != me)
+            if busy == 0:
+                return True
+            time.sleep(0.1)
+        return False
+    except Exception:  # noqa: BLE001
+        time.sleep(3.0)
+        return True
+
+
+def run_node_leg(n_gpus, args):
+    """ONE fresh process drives the first N GPUs (node-level checks, constructed baselines, the
+    manager's transitions).  A subprocess, because the release-context policy resets CUDA primary
+    contexts, which this process still shares with torch."""
+    idle = wait_for_idle_gpus(n_gpus)
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "CCM_ARENA_RESERVE_MB"):
+        env.pop(k, None)
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--node-leg", "--gpus", str(n_gpus)]
+    if args.no_transition:
+        cmd.append("--no-transition")
+    if args.no_baselines:
+        cmd.append("--no-baselines")
+    try:
+        proc = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=args.node_leg_timeout_s)
+        lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("NODE_LEG ")]
+        if not lines:
+            return {"error": f"node leg exit {proc.returncode}: {proc.stderr.strip()[-800:]}"}
+        out = json.loads(lines[-1][9:])
+        out.setdefault("node_checks", {})["other_ranks_gone_before_start"] = idle
+        return out
+    except Exception as exc:  # noqa: BLE001
+        return {"error": f"node leg failed: {exc}"}
+
+
+def node_leg(args):
+    n = args.gpus
     sys.path.insert(0, str(ROOT / "tests" / "fakes"))
+    os.environ["CCM_ALLOW_SIM"] = "1"
     import logging
 
-    import kubernetes
-    logging.disable(logging.CRITICAL)
-    from k8s_cc_manager_b200 import manager
+    from k8s_cc_manager_b200 import _native as N
+    from k8s_cc_manager_b200 import devices as D
+    L = N.lib()
+    check(L.ccm_init(N.BACKEND_CUDASIM), "ccm_init")
     out = {}
+    gpus = [d for d in D.find_gpus()[0] if d.is_gpu()][:n]
+    if len(gpus) < n:
+        raise SystemExit(f"node leg wants {n} GPUs, sees {len(gpus)}")
+
+    # ---- hardware proof for the in-process N-GPU launcher (tests/test_scrub_gpu.py:325-352) ----
+    t0 = time.perf_counter()
+    reports, wall_ms = D.scrub_and_verify_many(gpus, 0)
+    clean = all(r.clean for r in reports)
+    cov = [r.coverage for r in reports]
+    victim = gpus[-1]
+    L.ccm_sim_set(victim.index, b"scrub_inject", 5)
+    drill, _ = D.scrub_and_verify_many(gpus, 2 << 30)
+    L.ccm_sim_set(victim.index, b"scrub_inject", 0)
+    drill_ok = all((r.status == N.ERR_DIRTY and r.nonzero_bytes == 5) if r.bdf == victim.bdf else r.clean for r in drill)
+    out["node_checks"] = {
+        "gpus": n, "all_clean": clean, "coverage_min": min(cov), "coverage_max": max(cov),
+        "bytes_unreached_max": max(r.bytes_unreached for r in reports),
+        "first_gate_incl_context_creation_ms": (time.perf_counter() - t0) * 1e3, "first_gate_wall_ms": wall_ms,
+        "dirt_drill": {"victim": victim.bdf, "injected": 5, "statuses": [r.status for r in drill],
+                       "victim_counted": [r.nonzero_bytes for r in drill if r.bdf == victim.bdf][0], "ok": drill_ok},
+        "ok": bool(clean and min(cov) >= 0.99 and drill_ok)}
+    for g in gpus:
+        g.wait_scrub_released()
+
+    # ---- the node-level cold gate (one process, N threads), statistics ---------------------
+    v, c = [], []
+    for _ in range(args.node_gate_calls):
+        t0 = time.perf_counter()
+        reps, _ = D.scrub_and_verify_many(gpus, 0)
+        v.append(time.perf_counter() - t0)
+        for g in gpus:
+            g.wait_scrub_released()
+        c.append(time.perf_counter() - t0)
+        assert all(r.clean for r in reps)
+    out["node_checks"]["concurrent_gate_one_process"] = {
+        "verdict_s": stats(v), "cycle_s": stats(c), "bytes_total": sum(r.bytes_scrubbed for r in reps),
+        "acquire_host_ms_max": max(r.ms_acquire for r in reps), "gpu_span_ms_max": max(r.ms_gpu_span for r in reps)}
+
+    logging.disable(logging.CRITICAL)
     try:
-        L.ccm_sim_set(-1, b"cc_mode", 0)
-        c = kubernetes.reset_cluster()
-        from k8s_cc_manager_b200.drain_gate import COMPONENT_LABELS
-        labels = {k: "true" for k in COMPONENT_LABELS}
-        c.add_node("bench-node", labels)
-        os.environ["EVICT_OPERATOR_COMPONENTS"] = "true"
-        # this process shares its CUDA context with torch: do not reset it after the gate (a
-        # daemon does — CC_RELEASE_CUDA_CONTEXT=true — and then pays context creation per transition)
-        os.environ["CC_RELEASE_CUDA_CONTEXT"] = "false"
-        mgr = manager.CCManager("bench-node", "on", True)
-        for mode in ("on", "devtools", "off"):
-            t0 = time.perf_counter()
-            okay = mgr.set_cc_mode(mode)
-            dt = time.perf_counter() - t0
-            reps = mgr.last_transition.get("scrub") or []
-            out[f"to_{mode}"] = {"ok": bool(okay), "wall_s": dt,
-                                 "state_label": c.labels("bench-node").get("nvidia.com/cc.mode.state"),
-                                 "phase_seconds": mgr.last_transition.get("phase_seconds"),
-                                 "scrubbed_bytes": [r.bytes_scrubbed for r in reps] if isinstance(reps, list) else reps}
-        out["simulated"] = ["CC mode registers (sim backend; the box's driver-bound GPUs cannot be reset)",
-                            "reset/boot latency = 0 ms", "kubernetes API (in-memory fake, 0 ms RTT)"]
-        out["real"] = ["full-HBM scrub-and-verify gate on the GPU"]
+        if not args.no_transition:
+            out["transition"] = {"contexts_kept": measure_transitions(L, N, n, release_contexts=False)}
+        if not args.no_baselines:
+            out["baselines"] = constructed_baselines(L, N, n, args)
+        if not args.no_transition:
+            # LAST: this policy resets the CUDA primary contexts (torch, used by B2 above, is dead afterwards)
+            out["transition"]["daemon_default_release_contexts"] = measure_transitions(L, N, n, release_contexts=True)
+            out["transition"]["simulated"] = ["CC mode registers (cudasim backend; the box's driver-bound GPUs cannot be reset)",
+                                             "reset/boot latency = 0 ms", "kubernetes API (in-memory fake, 0 ms RTT)"]
+            out["transition"]["real"] = ["full-HBM scrub-and-verify gate on every GPU", "CUDA context creation / reset",
+                                         "driver memory management (cuMemCreate/Map/SetAccess/Unmap/Release)"]
     finally:
         logging.disable(logging.NOTSET)
+    print("NODE_LEG " + json.dumps(out), flush=True)
+    sys.stdout.flush()
+    os._exit(0)   # contexts may have been reset under torch: skip interpreter teardown
+
+
+def measure_transitions(L, N, n_gpus, release_contexts):
+    """BASELINE metric 1: wall-clock of CCManager.set_cc_mode off->on->devtools->off on the first N
+    GPUs, eviction-gated.  Simulated and reported as such: CC registers, reset/boot latency (0 ms),
+    the k8s API server (in-memory).  Real: the full-HBM scrub gate, CUDA contexts, driver memory work."""
+    import kubernetes
+    from k8s_cc_manager_b200 import devices as D
+    from k8s_cc_manager_b200 import manager
+    from k8s_cc_manager_b200.drain_gate import COMPONENT_LABELS
+    L.ccm_sim_set(-1, b"cc_mode", 0)
+    c = kubernetes.reset_cluster()
+    c.add_node("bench-node", {k: "true" for k in COMPONENT_LABELS})
+    os.environ["EVICT_OPERATOR_COMPONENTS"] = "true"
+    os.environ["CC_RELEASE_CUDA_CONTEXT"] = "true" if release_contexts else "false"
+    first_n = lambda: tuple(x[:n_gpus] if isinstance(x, list) else n_gpus for x in D.find_gpus())  # noqa: E731
+    mgr = manager.CCManager("bench-node", "on", True, device_source=first_n)
+    out = {"policy": "CC_RELEASE_CUDA_CONTEXT=" + ("true (daemon default)" if release_contexts else "false (contexts kept)"),
+           "gpus": n_gpus}
+    walls = []
+    for mode in ("on", "devtools", "off", "on", "off"):
+        t0 = time.perf_counter()
+        okay = mgr.set_cc_mode(mode)
+        dt = time.perf_counter() - t0
+        reps = mgr.last_transition.get("scrub") or []
+        key = f"to_{mode}" if f"to_{mode}" not in out else f"to_{mode}_again"
+        out[key] = {"ok": bool(okay), "wall_s": dt,
+                    "seconds_to_verdict": mgr.last_transition.get("seconds_to_verdict"),
+                    "state_label": c.labels("bench-node").get("nvidia.com/cc.mode.state"),
+                    "phase_seconds": mgr.last_transition.get("phase_seconds"),
+                    "scrubbed_bytes": [r.bytes_scrubbed for r in reps] if isinstance(reps, list) else reps,
+                    "coverage_min": min((r.coverage for r in reps), default=None) if isinstance(reps, list) else None}
+        walls.append(dt)
+    out["wall_s"] = stats(walls)
+    out["all_ok"] = all(v["ok"] for k, v in out.items() if k.startswith("to_"))
     return out
+
+
+def constructed_baselines(L, N, n_gpus, args):
+    """the reference has no scrub, so the baselines mirror its STRUCTURE (one Python
+    thread, GPUs one after another like reference main.py:504-529) with library calls only."""
+    import numpy as np
+    import torch
+    out = {}
+    # B2: serial cudaMemsetAsync + torch.count_nonzero per GPU (library-only GPU path)
+    t0 = time.perf_counter()
+    total = 0
+    for g in range(n_gpus):
+        torch.cuda.set_device(g)
+        free, _ = torch.cuda.mem_get_info(g)
+        want = (free - (4 << 30)) // (2 << 20) * (2 << 20)
+        buf = torch.empty(want, dtype=torch.uint8, device=f"cuda:{g}")
+        check(L.ccm_region_scrub(g, C.c_void_p(buf.data_ptr()), want, N.SCRUB_MEMSET, None, None, None), "memset")
+        torch.cuda.synchronize(g)
+        nz, step = 0, 256 << 20     # torch.count_nonzero on uint8 materialises an 8x temporary
+        for off in range(0, want, step):
+            nz += int(torch.count_nonzero(buf[off:off + step]))
+        assert nz == 0
+        total += want
+        del buf
+        torch.cuda.empty_cache()
+    dt = time.perf_counter() - t0
+    out["B2"] = {"wall_s": dt, "bytes_total": total, "value_gbs": 2.0 * total / dt / 1e9, "gpus": n_gpus,
+                 "what": "constructed: GPUs one after another, cudaMemsetAsync + torch.count_nonzero (256 MiB slices)"}
+    # B1: serial cudaMemset, verify on the HOST (256 MiB pinned D2H chunks + np.count_nonzero), bounded sample
+    sample = int(args.b1_sample_gib * 2**30)
+    chunk = 256 << 20
+    pinned = torch.empty(chunk, dtype=torch.uint8, pin_memory=True)
+    host = pinned.numpy()
+    t0 = time.perf_counter()
+    for g in range(n_gpus):
+        torch.cuda.set_device(g)
+        buf = torch.empty(sample, dtype=torch.uint8, device=f"cuda:{g}")
+        check(L.ccm_region_scrub(g, C.c_void_p(buf.data_ptr()), sample, N.SCRUB_MEMSET, None, None, None), "memset")
+        torch.cuda.synchronize(g)
+        nz = 0
+        for off in range(0, sample, chunk):
+            k = min(chunk, sample - off)
+            pinned[:k].copy_(buf[off:off + k])
+            torch.cuda.synchronize(g)
+            nz += int(np.count_nonzero(host[:k]))
+        assert nz == 0
+        del buf
+        torch.cuda.empty_cache()
+    dt = time.perf_counter() - t0
+    out["B1"] = {"wall_s": dt, "bytes_total": sample * n_gpus, "value_gbs": 2.0 * sample * n_gpus / dt / 1e9,
+                 "sample_bytes_per_gpu": sample,
+                 "what": "constructed: GPUs one after another, cudaMemset + host verify over PCIe "
+                         "(256 MiB pinned D2H + np.count_nonzero, one thread); bounded sample, throughput extrapolates linearly"}
+    # B0: the get-only plumbing path (BASELINE configs[0]) through the product
+    from k8s_cc_manager_b200 import devices as D
+    from k8s_cc_manager_b200 import manager
+    import kubernetes
+    c = kubernetes.reset_cluster()
+    c.add_node("bench-node", {})
+    L.ccm_sim_set(-1, b"cc_mode", 1)
+    os.environ["EVICT_OPERATOR_COMPONENTS"] = "false"
+    first_n = lambda: tuple(x[:n_gpus] if isinstance(x, list) else n_gpus for x in D.find_gpus())  # noqa: E731
+    mgr = manager.CCManager("bench-node", "on", True, device_source=first_n, scrub_mode="skip")
+    ts = []
+    for _ in range(200):
+        t0 = time.perf_counter()
+        assert mgr.set_cc_mode("on") is True
+        ts.append(time.perf_counter() - t0)
+    ref = None
+    try:
+        ref = json.loads((ROOT / "profiles" / "r1_config1_get_only.json").read_text())
+    except Exception:  # noqa: BLE001
+        pass
+    out["B0_get_only"] = {"product_us_median": statistics.median(ts) * 1e6, "gpus": n_gpus,
+                          "what": "configs[0]: set_cc_mode(mode) with every GPU already in `mode` (reference main.py:232-258): "
+                                  "N register reads + state label; sim registers, in-memory API",
+                          "reference_main_py_committed": ref and {k: ref[k] for k in ref if "us" in k or "note" in k or "what" in k},
+                          "reference_note": "the unmodified reference cannot run on the GPU box (/root/reference is not there); "
+                                            "its number was taken in the dev container: profiles/r1_config1_get_only.json"}
+    L.ccm_sim_set(-1, b"cc_mode", 0)
+    return out
+
+
+# --------------------------------------------------------------------------- sweep
+def run_sweep(args):
+    """BASELINE configs[4]: region sweep 1 GB -> max on this rank's GPU (all ranks concurrently under
+    torchrun): resident-kernel rates (CUDA events, best and median of 5) and the cold product call."""
+    import torch
+    from k8s_cc_manager_b200 import _native as N
+    from k8s_cc_manager_b200 import devices as D
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        os.environ.setdefault("CCM_ARENA_RESERVE_MB", "1024")
+    L = N.lib()
+    check(L.ccm_init(N.BACKEND_CUDASIM), "ccm_init")
+    dev = local
+    gpu = [d for d in D.find_gpus()[0] if d.is_gpu()][dev]
+    sizes = [int(x * 1e9) // (2 << 20) * (2 << 20) for x in (1, 2, 4, 8, 16, 32, 64, 128)] + [0]
+    rows = []
+    ms, nz = C.c_float(), C.c_uint64()
+    for want in sizes:
+        ai = N.ArenaInfo()
+        check(L.ccm_arena_acquire(dev, want, C.byref(ai)), "arena_acquire")
+        R = int(ai.bytes)
+        s_t, v_t, m_t = [], [], []
+        for i in range(7):
+            check(L.ccm_arena_fill(dev, 0xA5, None), "poison")
+            check(L.ccm_arena_scrub(dev, N.SCRUB_AUTO, None, None, C.byref(ms)), "scrub")
+            if i >= 2:
+                s_t.append(ms.value)
+            check(L.ccm_arena_verify(dev, N.VERIFY_AUTO, None, None, C.byref(nz), C.byref(ms)), "verify")
+            assert nz.value == 0
+            if i >= 2:
+                v_t.append(ms.value)
+            check(L.ccm_arena_scrub(dev, N.SCRUB_MEMSET, None, None, C.byref(ms)), "memset")
+            if i >= 2:
+                m_t.append(ms.value)
+        check(L.ccm_arena_release(dev), "release")
+        cold = []
+        for i in range(6):
+            if dist:
+                dist.barrier()
+            t0 = time.perf_counter()
+            rep = gpu.scrub_and_verify(want)
+            t1 = time.perf_counter()
+            gpu.wait_scrub_released()
+            if i:
+                cold.append((t1 - t0, time.perf_counter() - t0))
+        row = [float(R), R / min(s_t) / 1e6, R / statistics.median(s_t) / 1e6, R / min(v_t) / 1e6,
+               R / statistics.median(v_t) / 1e6, R / min(m_t) / 1e6, statistics.median(x[0] for x in cold) * 1e3,
+               statistics.median(x[1] for x in cold) * 1e3]
+        rows.append(row)
+    if dist:
+        t = torch.tensor(rows, dtype=torch.float64, device="cuda")
+        g = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        allr = [x.cpu().tolist() for x in g]
+        dist.destroy_process_group()
+    else:
+        allr = [rows]
+    if rank != 0:
+        return
+    table = []
+    for i in range(len(sizes)):
+        per = [allr[r][i] for r in range(world)]
+        table.append({"region_bytes_per_gpu": int(per[0][0]), "gpus": world,
+                      "scrub_gbs_per_gpu_best_min_over_gpus": min(p[1] for p in per),
+                      "scrub_gbs_per_gpu_median": statistics.median(p[2] for p in per),
+                      "verify_gbs_per_gpu_best_min_over_gpus": min(p[3] for p in per),
+                      "verify_gbs_per_gpu_median": statistics.median(p[4] for p in per),
+                      "memset_gbs_per_gpu_best": statistics.median(p[5] for p in per),
+                      "aggregate_scrub_gbs": sum(p[2] for p in per), "aggregate_verify_gbs": sum(p[4] for p in per),
+                      "cold_call_verdict_ms_max_over_gpus": max(p[6] for p in per),
+                      "cold_call_cycle_ms_max_over_gpus": max(p[7] for p in per)})
+    print(json.dumps({"sweep": table, "n_gpus": world, "unit": "GB/s", "kernels": list(N.default_kernels()),
+                      "how": "resident kernels: CUDA events around ONE launch, 5 timed passes after 2 warm passes, region "
+                             "re-poisoned before every scrub; memset = cudaMemsetAsync over the same region; cold call = "
+                             "Gpu.scrub_and_verify(bytes) wall-clock to verdict / to HBM handed back, median of 5"}), flush=True)
 
 
 def main():
@@ -422,15 +831,26 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--gib", type=float, default=0.0, help="region per GPU in GiB (0 = all mappable HBM)")
     ap.add_argument("--scrub", default="auto", choices=("auto", "st128", "st256", "tma", "memset"))
-    ap.add_argument("--verify", default="auto", choices=("auto", "ld128", "ld256", "tma"))
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--verify", default="auto", choices=("auto", "ld128", "ld256"))
+    ap.add_argument("--e2e-steps", type=int, default=15)
     ap.add_argument("--cpu-sample-gib", type=float, default=8.0)
-    ap.add_argument("--cpu-budget-s", type=float, default=10.0)
+    ap.add_argument("--cpu-passes", type=int, default=40)
+    ap.add_argument("--b1-sample-gib", type=float, default=2.0)
+    ap.add_argument("--node-gate-calls", type=int, default=7)
+    ap.add_argument("--node-leg-timeout-s", type=float, default=600.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-transition", action="store_true")
+    ap.add_argument("--no-baselines", action="store_true")
+    ap.add_argument("--no-node-leg", action="store_true")
     ap.add_argument("--no-host-roundtrip", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="region sweep 1 GB -> max instead of the bench line")
+    ap.add_argument("--node-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.node_leg:
+        node_leg(args)
+    elif args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)

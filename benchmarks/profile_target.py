@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
 """Small, fixed launch sequence for ncu (run under gpurun, one GPU).
 
-  python benchmarks/profile_target.py --gib 4 --seq memset,st256,st256:4:512:4,tma,ld256,vtma
+  python benchmarks/profile_target.py --gib 4 --seq memset,st256,st256:4:512:4,tma,ld256,vauto
 
 Each item is variant[:ctas_per_sm:threads:unroll[:policy[:tile[:schedule]]]]; scrub variants
-zero the arena, verify variants (ld128, ld256, vtma) count it.  Prints CUDA-event
+zero the arena, verify variants (ld128, ld256, vauto) count it.  Prints CUDA-event
 times so the same command can be timed outside the profiler.
 """
 from __future__ import annotations
@@ -19,7 +19,7 @@ from k8s_cc_manager_b200 import _native as N  # noqa: E402
 
 SCRUB = {"memset": N.SCRUB_MEMSET, "st128": N.SCRUB_ST128, "st256": N.SCRUB_ST256, "tma": N.SCRUB_TMA,
          "auto": N.SCRUB_AUTO}
-VERIFY = {"ld128": N.VERIFY_LD128, "ld256": N.VERIFY_LD256, "vtma": N.VERIFY_TMA, "vauto": N.VERIFY_AUTO}
+VERIFY = {"ld128": N.VERIFY_LD128, "ld256": N.VERIFY_LD256, "vauto": N.VERIFY_AUTO}
 
 
 def main():

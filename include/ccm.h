@@ -268,6 +268,12 @@ int ccm_device_release(int dev);
 /* Concurrent form for `n` devices (one host thread each); *wall_ms = host wall-clock. */
 int ccm_device_release_many(int n, const int* devs, double* wall_ms);
 
+/* Names of the two kernels AUTO launches, as ncu prints them, separated by ';' —
+ * "scrub_st256_fast_kernel<512, 8, 0>;verify_ld256_fast_kernel<1024, 4, 2>".  Built from the
+ * same compile-time constants as the launches, so tools that key measurements by kernel name
+ * (bench.py's roofline.traffic <- profiles/traffic.json) notice when the default changes. */
+const char* ccm_default_kernels(void);
+
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t ccm_kernel_launches(void);
 

@@ -147,6 +147,7 @@ _SIGNATURES = {
     "ccm_device_release": (C.c_int, [C.c_int]),
     "ccm_device_release_many": (C.c_int, [C.c_int, _P(C.c_int), _P(C.c_double)]),
     "ccm_kernel_launches": (C.c_uint64, []),
+    "ccm_default_kernels": (C.c_char_p, []),
     "ccm_sim_topology": (C.c_int, [C.c_int, C.c_int]),
     "ccm_sim_set": (C.c_int, [C.c_int, C.c_char_p, C.c_int64]),
     "ccm_sim_get": (C.c_int, [C.c_int, C.c_char_p, _P(C.c_int64)]),
@@ -189,6 +190,11 @@ def lib() -> C.CDLL:
             raise NativeLibraryError(f"{LIB_PATH}: ABI version {handle.ccm_abi_version()} != {ABI_VERSION}")
         _lib = handle
     return _lib
+
+
+def default_kernels() -> tuple:
+    """(scrub kernel, verify kernel) AUTO launches, named the way ncu prints them."""
+    return tuple(lib().ccm_default_kernels().decode().split(";"))
 
 
 def strerror(status: int) -> str:

@@ -606,6 +606,7 @@ int ccm_device_release_many(int n, const int* devs, double* wall_ms) {
 }
 
 uint64_t ccm_kernel_launches(void) { return kernel_launches(); }
+const char* ccm_default_kernels(void) { return default_kernel_names(); }
 
 // ------------------------------------------------------------------ sim knobs
 int ccm_sim_topology(int n_gpus, int n_switches) {

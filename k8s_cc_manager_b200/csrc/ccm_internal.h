@@ -46,6 +46,7 @@ int engine_region_verify(ScrubEngine*, const void* dptr, uint64_t bytes, int var
 int engine_host_roundtrip(ScrubEngine*, void* host_buf, uint64_t bytes, uint64_t dev_offset,
                           int sv, int vv, uint64_t* pre, uint64_t* post);
 uint64_t kernel_launches();
+const char* default_kernel_names();
 // Tears down the engine of a CUDA ordinal (if any) and resets its primary context.
 int engine_teardown(int ordinal);
 

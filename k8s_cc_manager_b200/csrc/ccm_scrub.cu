@@ -12,6 +12,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -123,6 +124,16 @@ static constexpr int kFastScrubThreads = 512, kFastScrubPer = 8;
 static constexpr int kFastVerifyThreads = 1024, kFastVerifyPer = 4;
 #define CCM_FAST_SCRUB scrub_st256_fast_kernel<kFastScrubThreads, kFastScrubPer, kPolDefault>
 #define CCM_FAST_VERIFY verify_ld256_fast_kernel<kFastVerifyThreads, kFastVerifyPer, kPolStreaming>
+
+const char* default_kernel_names() {
+  static const std::string names = [] {
+    char b[160];
+    snprintf(b, sizeof b, "scrub_st256_fast_kernel<%d, %d, %d>;verify_ld256_fast_kernel<%d, %d, %d>",
+             kFastScrubThreads, kFastScrubPer, (int)kPolDefault, kFastVerifyThreads, kFastVerifyPer, (int)kPolStreaming);
+    return std::string(b);
+  }();
+  return names.c_str();
+}
 
 int ScrubEngine::init() {
   if (ready) return CCM_OK;
@@ -791,7 +802,7 @@ static bool async_release_enabled() { return env_u64("CCM_ASYNC_RELEASE", 1) != 
 //
 // * chunk sizes grow 1, 2, 4, 8, 16, 16, ... GiB so the first stores are issued ~1 ms into the
 //   call; a few large chunks keep the driver's per-mapping costs (unmap!) down;
-// * with bytes == 0 the last CCM_ARENA_RESERVE_MB of free HBM (the "tail zone") are taken in
+// * with bytes == 0 the last CCM_VMM_TAIL_MB (256) of free HBM (the "tail zone") are taken in
 //   32 MiB -> 2 MiB granules until the driver says out-of-memory, so the region is everything
 //   the context can reach, not "free minus a safety margin";
 // * every chunk is read back right after it was zeroed, while the host is still mapping the
@@ -824,7 +835,7 @@ static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t injec
   const uint64_t va_bytes = want_max ? (uint64_t)fr / gran * gran : (bytes + gran - 1) / gran * gran;
   if (va_bytes == 0) { set_error("no free HBM to scrub (free=%zu)", fr); return CCM_ERR_NOMEM; }
   // tail zone: where running out of memory is expected and simply ends the region
-  uint64_t tail_zone = want_max ? env_u64("CCM_ARENA_RESERVE_MB", 256) * kMiB / gran * gran : 0;
+  uint64_t tail_zone = want_max ? env_u64("CCM_VMM_TAIL_MB", 256) * kMiB / gran * gran : 0;
   if (tail_zone > va_bytes) tail_zone = va_bytes;
   uint64_t main_end = va_bytes - tail_zone;
   uint64_t max_chunk = env_u64("CCM_VMM_CHUNK_MB", 16384) * kMiB / gran * gran;

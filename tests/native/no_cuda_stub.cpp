@@ -23,5 +23,6 @@ int engine_region_scrub(ScrubEngine*, void*, uint64_t, int, const ccm_launch_cfg
 int engine_region_verify(ScrubEngine*, const void*, uint64_t, int, const ccm_launch_cfg*, void*, uint64_t*, float*) { return CCM_ERR_NO_CUDA; }
 int engine_host_roundtrip(ScrubEngine*, void*, uint64_t, uint64_t, int, int, uint64_t*, uint64_t*) { return CCM_ERR_NO_CUDA; }
 uint64_t kernel_launches() { return 0; }
+const char* default_kernel_names() { return ""; }
 int engine_teardown(int) { return CCM_OK; }
 }  // namespace ccm

