@@ -138,35 +138,55 @@ def host_threads() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def cpu_arm(sample_gib: float, passes: int, warm: int):
-    """oracle/scrub_oracle.c (memset + byte-wise non-zero count) on the host cores — the ONLY place
-    bench.py executes oracle code, and only as the baseline.  Thread i is pinned to the i-th allowed
-    CPU and first-touches its own slice, so every slice lives on the NUMA node that streams it
-    (round 1 first-touched from one thread: 26 GB/s on one box, 112 GB/s on another)."""
+def cpu_arm(sample_gib: float, passes: int, warm: int, probe: bool = False):
+    """oracle/scrub_oracle.c (scrub + byte-wise non-zero count) on the host cores — the ONLY place
+    bench.py executes oracle code, and only as the baseline.  The baseline gets every help a careful CPU
+    implementation would take (a straw man inflates the headline ratio — VERDICT r1 weak #3): a
+    persistent pool, thread i pinned to the i-th allowed CPU, first-touching and then streaming its OWN
+    slice (NUMA-local; round 1 first-touched from one thread: 26 GB/s on one box, 112 on another), and the
+    faster of {libc memset, non-temporal stores} x {all hardware threads, one per core} picked in the
+    untimed warm-up."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import numpy as np
     import scrub_oracle as SO
 
-    threads = host_threads()
+    hw = host_threads()
     nbytes = int(sample_gib * 2**30)
     buf = np.empty(nbytes, dtype=np.uint8)
-    SO.fill_mt_c(buf, threads, 0xA5, pin=True)                       # parallel first touch + poison (untimed)
-    assert SO.scrub_verify_mt_c(buf, threads, scrub=False, pin=True) == nbytes
-    for _ in range(max(1, warm)):
-        assert SO.scrub_verify_mt_c(buf, threads, pin=True) == 0      # warm passes (untimed)
-    times = []
-    for _ in range(passes):
-        t0 = time.perf_counter()
-        nz = SO.scrub_verify_mt_c(buf, threads, pin=True)
-        times.append(time.perf_counter() - t0)
-        assert nz == 0
+    candidates = []
+    for threads in sorted({hw, max(1, hw // 2)}, reverse=True):
+        with SO.Pool(buf, threads, pin=True) as pool:
+            assert pool.poison() == nbytes                              # parallel first touch (untimed)
+            for stream in (False, True):
+                assert pool.scrub_verify(stream) == 0
+                ts = []
+                for _ in range(max(2, warm)):
+                    t0 = time.perf_counter()
+                    assert pool.scrub_verify(stream) == 0
+                    ts.append(time.perf_counter() - t0)
+                candidates.append({"threads": threads, "scrub": "nt-stores" if stream else "memset",
+                                   "gbs_best": 2.0 * nbytes / min(ts) / 1e9, "gbs_median": 2.0 * nbytes / statistics.median(ts) / 1e9})
+    pick = max(candidates, key=lambda c: c["gbs_median"])
+    threads, stream = pick["threads"], pick["scrub"] == "nt-stores"
+    with SO.Pool(buf, threads, pin=True) as pool:
+        assert pool.poison() == nbytes                                  # slices re-touched by THESE threads
+        assert pool.scrub_verify(stream) == 0
+        times = []
+        for _ in range(passes):
+            t0 = time.perf_counter()
+            nz = pool.scrub_verify(stream)
+            times.append(time.perf_counter() - t0)
+            assert nz == 0
     rates = [2.0 * nbytes / t / 1e9 for t in times]
-    sample = (f"{sample_gib:g} GiB host buffer, {passes} timed passes of memset + byte-wise count on {threads} pinned "
-              f"pthreads, each first-touching and then streaming its own slice (oracle/scrub_oracle.c; the reference has "
-              f"no scrub to time); {SO.numa_layout()}")
-    return {"value": 2.0 * nbytes * passes / sum(times) / 1e9, "best": max(rates), "median": statistics.median(rates),
-            "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": sum(times),
-            "bytes_per_pass": nbytes, "passes": passes}
+    sample = (f"{sample_gib:g} GiB host buffer, {passes} timed passes of scrub ({pick['scrub']}) + byte-wise count on a "
+              f"persistent pool of {threads} pinned pthreads (of {hw} hardware threads), each first-touching and then "
+              f"streaming its own slice (oracle/scrub_oracle.c; the reference has no scrub to time); {SO.numa_layout()}")
+    out = {"value": 2.0 * nbytes * passes / sum(times) / 1e9, "best": max(rates), "median": statistics.median(rates),
+           "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": sum(times),
+           "bytes_per_pass": nbytes, "passes": passes, "tuning": candidates}
+    if probe:
+        print(json.dumps(out), flush=True)
+    return out
 
 
 def run_reference_arm(args):
@@ -185,7 +205,7 @@ def run_reference_arm(args):
                        "sample": cb["sample"], "same_config": False,
                        "note": f"bounded sample: {args.cpu_sample_gib:g} GiB per step instead of the GPU arm's ~190.8 GB per GPU "
                                "(a bandwidth-bound loop: GB/s does not depend on the length)"},
-            "cpu_baseline": {k: cb[k] for k in ("value", "best", "median", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: cb[k] for k in ("value", "best", "median", "unit", "cores", "kind", "sample", "tuning")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -844,9 +864,12 @@ def main():
     ap.add_argument("--no-node-leg", action="store_true")
     ap.add_argument("--no-host-roundtrip", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="region sweep 1 GB -> max instead of the bench line")
+    ap.add_argument("--cpu-probe", action="store_true", help="only the CPU arm, with its tuning table")
     ap.add_argument("--node-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.node_leg:
+    if args.cpu_probe:
+        cpu_arm(args.cpu_sample_gib, passes=args.cpu_passes, warm=3, probe=True)
+    elif args.node_leg:
         node_leg(args)
     elif args.sweep:
         run_sweep(args)

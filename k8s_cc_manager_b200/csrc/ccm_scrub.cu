@@ -726,6 +726,10 @@ int engine_arena_rw(ScrubEngine* e, uint64_t offset, void* host, uint64_t bytes,
     return CCM_ERR_INVALID;
   }
   CCM_CUDA(cudaSetDevice(e->ordinal));
+  // Pokes and peeks are synchronous copies on the legacy stream; the scrub/verify launches they
+  // interleave with run on NON-BLOCKING streams (the engine's, or the caller's) and are not ordered
+  // against it — a 25 ms full-arena scrub still in flight would overwrite a byte poked "after" it.
+  CCM_CUDA(cudaDeviceSynchronize());
   uint8_t* h = (uint8_t*)host;
   uint64_t seg_start = 0;
   for (auto& s : e->segs) {

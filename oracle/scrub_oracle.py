@@ -96,6 +96,12 @@ def clib() -> C.CDLL:
         lib.ccm_oracle_scrub_verify_mt_pinned.restype = C.c_uint64
         lib.ccm_oracle_fill_mt.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int]
         lib.ccm_oracle_fill_mt.restype = None
+        lib.ccm_oracle_pool_create.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+        lib.ccm_oracle_pool_create.restype = C.c_void_p
+        lib.ccm_oracle_pool_pass.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.ccm_oracle_pool_pass.restype = C.c_uint64
+        lib.ccm_oracle_pool_destroy.argtypes = [C.c_void_p]
+        lib.ccm_oracle_pool_destroy.restype = None
         _lib = lib
     return _lib
 
@@ -142,3 +148,31 @@ def numa_layout() -> str:
         except OSError:
             pass
     return f"{len(nodes)} NUMA node(s): " + "; ".join(nodes) if nodes else "NUMA layout unknown"
+
+
+class Pool:
+    """Persistent pinned worker pool over one host buffer (bench.py's CPU arm): thread i owns slice i
+    for its first touch and for every pass.  stream=True scrubs with non-temporal stores instead of
+    libc memset (same bytes, no write-allocate reads)."""
+
+    def __init__(self, buf: np.ndarray, threads: int, pin: bool = True):
+        self.buf, self.threads = buf, threads
+        self._h = clib().ccm_oracle_pool_create(buf.ctypes.data, buf.nbytes, threads, 1 if pin else 0)
+
+    def poison(self) -> int:
+        """first touch: fill 0xA5, return the count (== nbytes)"""
+        return int(clib().ccm_oracle_pool_pass(self._h, 4 | 2, 0))
+
+    def scrub_verify(self, stream: bool = False) -> int:
+        return int(clib().ccm_oracle_pool_pass(self._h, 1 | 2, 1 if stream else 0))
+
+    def close(self) -> None:
+        if self._h:
+            clib().ccm_oracle_pool_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

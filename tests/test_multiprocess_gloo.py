@@ -115,3 +115,4 @@ def test_cpu_arm_reports_best_and_median_with_numa_layout():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["passes"] == 3
     assert cb["best"] >= cb["median"] > 0 and cb["value"] > 0
     assert "NUMA" in cb["sample"] and "pinned" in cb["sample"]
+    assert {c["scrub"] for c in cb["tuning"]} == {"memset", "nt-stores"}
