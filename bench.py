@@ -483,7 +483,7 @@ def run_ours(args):
                 "steps": e2e_steps, "warmup": max(3, args.warmup),
                 "seconds_per_step": statistics.median(cycle),
                 "cycle_s": cold["cycle_s"], "verdict_s": cold["verdict_s"],
-                "verdict_value": cold["verdict_value_gbs"],
+                "value_mean": cold["value_mean_gbs"], "verdict_value": cold["verdict_value_gbs"],
                 "loop_wall_s": loop_s,
                 "phases": phases,
                 "ms_verdict_each_step": [round(x * 1e3, 2) for x in verdict],
@@ -494,8 +494,9 @@ def run_ours(args):
                                                  "bytes_unreached": last.bytes_unreached, "coverage": last.coverage},
                 "api": "k8s_cc_manager_b200.devices.Gpu.scrub_and_verify -> ccm_scrub_verify (C ABI); "
                        "Gpu.wait_scrub_released -> ccm_scrub_release_wait",
-                "note": "value = 2 x bytes / sum over calls of the max-over-ranks CYCLE time (call start -> verdict -> "
-                        "HBM handed back); every call starts on a barrier.  verdict_s is what a transition waits "
+                "note": "value = 2 x bytes of one call (all ranks) / MEDIAN over calls of the max-over-ranks CYCLE time (call "
+                        "start -> verdict -> HBM handed back; value_mean uses the sum instead); every call starts on a "
+                        "barrier.  verdict_s is what a transition waits "
                         "for: the unmap/release runs on libccm's reaper thread.  Back-to-back cold calls are the "
                         "driver's worst case (it re-allocates memory it is still scrubbing after the last free).  "
                         "No host-resident input exists on this path."},
@@ -576,6 +577,9 @@ def node_leg(args):
     n = args.gpus
     sys.path.insert(0, str(ROOT / "tests" / "fakes"))
     os.environ["CCM_ALLOW_SIM"] = "1"
+    # rank 0's parent process is still alive with its own CUDA context (~0.8 GiB) on GPU 0, so that
+    # GPU reaches ~99.2 % instead of the 99.66 % of a GPU with no other tenant: keep a margin under it
+    os.environ.setdefault("CC_SCRUB_MIN_COVERAGE", "0.985")
     import logging
 
     from k8s_cc_manager_b200 import _native as N

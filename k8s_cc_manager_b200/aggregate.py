@@ -65,7 +65,8 @@ def aggregate_cold_calls(all_rows) -> dict:
     8-byte count is on the host; cycle_s = call start -> the HBM is back with the driver.  A node is
     done when its SLOWEST GPU is done, so each call contributes the max over ranks; the spread is
     taken over calls (never a mean of five with one outlier — VERDICT r1 weak #2).
-    value = (bytes zeroed + read back by all ranks in all calls) / sum over calls of the max cycle."""
+    value_gbs = (bytes zeroed + read back by all ranks in ONE call) / MEDIAN over calls of the max cycle;
+    value_mean_gbs = the same bytes over all calls / SUM of the max cycles (what a mean would say)."""
     world, calls = len(all_rows), len(all_rows[0])
     verdict = [max(all_rows[r][i][0] for r in range(world)) for i in range(calls)]
     cycle = [max(all_rows[r][i][1] for r in range(world)) for i in range(calls)]
@@ -74,6 +75,7 @@ def aggregate_cold_calls(all_rows) -> dict:
         "world": world, "calls": calls, "bytes_total": total_bytes,
         "verdict_s_each": verdict, "cycle_s_each": cycle,
         "verdict_s": spread(verdict), "cycle_s": spread(cycle),
-        "value_gbs": 2.0 * total_bytes / sum(cycle) / 1e9,
+        "value_gbs": 2.0 * (total_bytes / calls) / spread(cycle)["median"] / 1e9,
+        "value_mean_gbs": 2.0 * total_bytes / sum(cycle) / 1e9,
         "verdict_value_gbs": 2.0 * (total_bytes / calls) / spread(verdict)["median"] / 1e9,
     }
