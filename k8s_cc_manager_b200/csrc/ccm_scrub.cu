@@ -850,6 +850,8 @@ static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t injec
   uint64_t tail_chunk = 32 * kMiB / gran * gran;
   if (tail_chunk < gran) tail_chunk = gran;
   const bool interleave = env_u64("CCM_INTERLEAVE_VERIFY", 1) != 0;
+  // CCM_MAP_FIRST=1: map the whole range before the first launch (no overlap of mapping and kernels)
+  const bool map_first = env_u64("CCM_MAP_FIRST", 0) != 0;
 
   VmmMapping m;
   if (api.AddressReserve(&m.base, va_bytes, 0, 0, 0) != CUDA_SUCCESS) return CCM_ERR_UNSUPPORTED;
@@ -923,11 +925,12 @@ static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t injec
     m.handles.push_back(h);
     m.mapped = off + n;
     // tail-zone granules are scrubbed with ONE launch pair once the zone is mapped
-    if (!in_tail) rc = enqueue(off, n);
+    if (!in_tail && !map_first) rc = enqueue(off, n);
     off += n;
     if (!in_tail && chunk < max_chunk) { chunk *= 2; if (chunk > max_chunk) chunk = max_chunk; }
   }
-  if (rc == CCM_OK && in_tail && m.mapped > tail_start) rc = enqueue(tail_start, m.mapped - tail_start);
+  if (rc == CCM_OK && map_first) { if (m.mapped) rc = enqueue(0, m.mapped); }
+  else if (rc == CCM_OK && in_tail && m.mapped > tail_start) rc = enqueue(tail_start, m.mapped - tail_start);
   if (rc == CCM_OK && !interleave) {
     cudaEventRecord(e->ev[1], st);
     rc = verify_range(e, (const void*)m.base, m.mapped, CCM_VERIFY_AUTO, nullptr, st);

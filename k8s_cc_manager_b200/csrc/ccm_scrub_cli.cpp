@@ -75,6 +75,7 @@ int main(int argc, char** argv) {
            (unsigned long long)r.device_free_before, (unsigned long long)r.bytes_unreached, r.ms_release_wait, r.ms_gpu_span);
   }
   printf("]}\n");
+  fflush(stdout);  // the verdict is out BEFORE the contexts are torn down: a parent can act on it right away
   ccm_device_release_many((int)devs.size(), devs.data(), nullptr);  // joins the deferred HBM release, drops the contexts
   return clean ? 0 : 3;
 }
