@@ -482,14 +482,16 @@ static ScrubEngine* engine_of_ordinal(int ordinal, int* rc) {
   return e;
 }
 
-int ccm_scrub_verify(int dev, uint64_t bytes, ccm_scrub_result* out) {
+static int scrub_verify_one(int dev, uint64_t bytes, bool node_fanout, ccm_scrub_result* out) {
   if (out) { memset(out, 0, sizeof *out); out->bytes_requested = bytes; }
   uint64_t inject = 0;
   int rc = sim_scrub_hook(dev, &inject);
   ScrubEngine* e = rc ? nullptr : engine_of_dev(dev, &rc);
   if (!e) { if (out) out->status = rc; return rc; }
-  return engine_scrub_verify(e, bytes, inject, out);
+  return engine_scrub_verify(e, bytes, inject, node_fanout, out);
 }
+
+int ccm_scrub_verify(int dev, uint64_t bytes, ccm_scrub_result* out) { return scrub_verify_one(dev, bytes, false, out); }
 
 int ccm_scrub_release_wait(int dev, double* ms_release, double* ms_waited) {
   if (ms_release) *ms_release = 0;
@@ -506,7 +508,7 @@ int ccm_scrub_verify_many(int n, const int* devs, uint64_t bytes, ccm_scrub_resu
   th.reserve(n);
   for (int i = 0; i < n; ++i)
     th.emplace_back([&, i] {
-      int rc = ccm_scrub_verify(devs[i], bytes, &out[i]);
+      int rc = scrub_verify_one(devs[i], bytes, n > 1, &out[i]);
       if (rc) errs[i] = last_error();
     });
   for (auto& t : th) t.join();

@@ -36,7 +36,8 @@ int engine_arena_fill_random(ScrubEngine*, uint64_t seed, void* stream);
 int engine_arena_rw(ScrubEngine*, uint64_t offset, void* host, uint64_t bytes, bool write);
 // inject: fault drill (sim key "scrub_inject") — that many bytes are poisoned AFTER the scrub and
 // BEFORE the read-back (first / unaligned / middle / last byte of each chunk), so the verdict must be DIRTY.
-int engine_scrub_verify(ScrubEngine*, uint64_t bytes, uint64_t inject, ccm_scrub_result* out);
+// node_fanout: the call is one of several running concurrently in THIS process (ccm_scrub_verify_many).
+int engine_scrub_verify(ScrubEngine*, uint64_t bytes, uint64_t inject, bool node_fanout, ccm_scrub_result* out);
 // Joins the background release of the last product call (no-op when none is pending).
 int engine_release_wait(ScrubEngine*, double* ms_release, double* ms_waited);
 int engine_region_scrub(ScrubEngine*, void* dptr, uint64_t bytes, int variant,

@@ -813,7 +813,7 @@ static bool async_release_enabled() { return env_u64("CCM_ASYNC_RELEASE", 1) != 
 //   next one (the GPU would otherwise idle: mapping 16 GiB takes as long as scrubbing it);
 // * the verdict is returned as soon as the 8-byte count is on the host; cuMemUnmap/cuMemRelease
 //   (0.33 ms/GiB, serialised node-wide by the driver) run on the engine's reaper thread.
-static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t inject, ccm_scrub_result* r) {
+static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t inject, bool node_fanout, ccm_scrub_result* r) {
   const VmmApi& api = vmm();
   if (!api.ok) return CCM_ERR_UNSUPPORTED;
   std::lock_guard<std::mutex> g(e->mu);
@@ -850,8 +850,12 @@ static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t injec
   uint64_t tail_chunk = 32 * kMiB / gran * gran;
   if (tail_chunk < gran) tail_chunk = gran;
   const bool interleave = env_u64("CCM_INTERLEAVE_VERIFY", 1) != 0;
-  // CCM_MAP_FIRST=1: map the whole range before the first launch (no overlap of mapping and kernels)
-  const bool map_first = env_u64("CCM_MAP_FIRST", 0) != 0;
+  // Map the whole range before the first launch (no overlap of mapping and kernels)?  One GPU per
+  // process: no — pipelining wins (verdict after 55 ms instead of ~75 ms).  Several GPUs driven from
+  // ONE process (ccm_scrub_verify_many): yes — VMM calls interleaved with launches on 8 devices of one
+  // process take 0.7 s to the verdict, mapping first takes 0.22 s (profiles/r2_node_gate_modes_8gpu.log).
+  // CCM_MAP_FIRST=0/1 overrides.
+  const bool map_first = env_u64("CCM_MAP_FIRST", node_fanout ? 1 : 0) != 0;
 
   VmmMapping m;
   if (api.AddressReserve(&m.base, va_bytes, 0, 0, 0) != CUDA_SUCCESS) return CCM_ERR_UNSUPPORTED;
@@ -991,7 +995,7 @@ int engine_release_wait(ScrubEngine* e, double* ms_release, double* ms_waited) {
 }
 
 // --------------------------------------------------------------- product call
-int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, uint64_t inject, ccm_scrub_result* out) {
+int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, uint64_t inject, bool node_fanout, ccm_scrub_result* out) {
   const double t0 = now_ms();
   ccm_scrub_result r;
   memset(&r, 0, sizeof r);
@@ -1000,7 +1004,7 @@ int engine_scrub_verify(ScrubEngine* e, uint64_t bytes, uint64_t inject, ccm_scr
   r.scrub_variant = resolve_scrub_variant(CCM_SCRUB_AUTO);
   r.verify_variant = resolve_verify_variant(CCM_VERIFY_AUTO);
   int rc = CCM_ERR_UNSUPPORTED;
-  if (env_u64("CCM_PIPELINE", 1) != 0) rc = scrub_verify_pipelined(e, bytes, inject, &r);
+  if (env_u64("CCM_PIPELINE", 1) != 0) rc = scrub_verify_pipelined(e, bytes, inject, node_fanout, &r);
   if (rc == CCM_ERR_UNSUPPORTED) {
     // plain path: one cudaMalloc'ed arena, whole-arena scrub, whole-arena verify
     ccm_arena_info ai;

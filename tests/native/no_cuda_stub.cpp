@@ -17,7 +17,7 @@ int engine_arena_step_times(ScrubEngine*, int, float*, float*, int*) { return CC
 int engine_arena_fill(ScrubEngine*, int, void*) { return CCM_ERR_NO_CUDA; }
 int engine_arena_fill_random(ScrubEngine*, uint64_t, void*) { return CCM_ERR_NO_CUDA; }
 int engine_arena_rw(ScrubEngine*, uint64_t, void*, uint64_t, bool) { return CCM_ERR_NO_CUDA; }
-int engine_scrub_verify(ScrubEngine*, uint64_t, uint64_t, ccm_scrub_result*) { return CCM_ERR_NO_CUDA; }
+int engine_scrub_verify(ScrubEngine*, uint64_t, uint64_t, bool, ccm_scrub_result*) { return CCM_ERR_NO_CUDA; }
 int engine_release_wait(ScrubEngine*, double*, double*) { return CCM_ERR_NO_CUDA; }
 int engine_region_scrub(ScrubEngine*, void*, uint64_t, int, const ccm_launch_cfg*, void*, float*) { return CCM_ERR_NO_CUDA; }
 int engine_region_verify(ScrubEngine*, const void*, uint64_t, int, const ccm_launch_cfg*, void*, uint64_t*, float*) { return CCM_ERR_NO_CUDA; }
