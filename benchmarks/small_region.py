@@ -4,7 +4,7 @@ Times ONE launch of the default scrub / verify kernel with CUDA events (best and
 5 warm passes), per launch shape (CCM_FAST_*_SHAPE = threads x vectors x CTAs/SM), plus the scrub+verify
 PAIR (one event bracket around both launches) with and without programmatic dependent launch.
 
-  python benchmarks/small_region.py --gb 1,4 --shapes-scrub 512x8x1,512x4x2 --shapes-verify 1024x4x1,512x4x2
+  python benchmarks/small_region.py --gb 1,4 (round-2 result: launch shape is irrelevant — profiles/r2_small_region_shapes.log — so the library keeps ONE instantiation; the shape switches of this script only work on a build that carries more)
 """
 from __future__ import annotations
 
@@ -64,16 +64,16 @@ def worker(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gb", default="1,4")
-    ap.add_argument("--shapes-scrub", default="512x8x1,512x4x1,512x4x2,256x8x2,256x4x4,1024x4x1")
-    ap.add_argument("--shapes-verify", default="1024x4x1,1024x2x1,512x4x2,512x8x1,256x8x2,256x8x4")
+    ap.add_argument("--shapes-scrub", default="")
+    ap.add_argument("--shapes-verify", default="")
     ap.add_argument("--worker", action="store_true")
     args = ap.parse_args()
     if args.worker:
         return worker(args)
     runs = [({}, "default")]
-    for sh in args.shapes_scrub.split(","):
+    for sh in filter(None, args.shapes_scrub.split(",")):
         runs.append(({"CCM_FAST_SCRUB_SHAPE": sh}, f"scrub {sh}"))
-    for sh in args.shapes_verify.split(","):
+    for sh in filter(None, args.shapes_verify.split(",")):
         runs.append(({"CCM_FAST_VERIFY_SHAPE": sh}, f"verify {sh}"))
     runs.append(({"CCM_PDL": "1"}, "default + PDL"))
     for env, tag in runs:

@@ -376,16 +376,6 @@ static cudaError_t launch_fast(void (*kernel)(KArgs...), int grid, int threads, 
   return cudaLaunchKernelEx(&lc, kernel, KArgs(args)...);
 }
 
-// Launch shape of the default kernels: threads x vectors-per-thread x CTAs-per-SM.  The full-arena
-// shape is the compile-time default; CCM_FAST_SCRUB_SHAPE / CCM_FAST_VERIFY_SHAPE ("512x4x2") select
-// another instantiation for experiments (benchmarks/small_region.py).
-static void fast_shape_for(uint64_t bytes, bool scrub, int* threads, int* per, int* cps) {
-  (void)bytes;
-  const char* v = getenv(scrub ? "CCM_FAST_SCRUB_SHAPE" : "CCM_FAST_VERIFY_SHAPE");
-  int t = 0, p = 0, c = 0;
-  if (v && sscanf(v, "%dx%dx%d", &t, &p, &c) == 3 && t > 0 && p > 0 && c > 0) { *threads = t; *per = p; *cps = c; }
-}
-
 // True when (variant, cfg) resolves to the compile-time-shape default kernel.
 static bool is_fast_scrub(int variant, const ccm_launch_cfg* cfg) {
   return cfg == nullptr && resolve_scrub_variant(variant) == CCM_SCRUB_ST256;
@@ -420,15 +410,8 @@ static int scrub_range(ScrubEngine* e, void* p, uint64_t n, int variant, const c
       if (cfg == nullptr) {
         // library default: compile-time shape (148 persistent CTAs x 512 threads, 8 x STG.256 per
         // thread per 128 KiB grab) — scrub_st256_fast_kernel
-        int T = kFastScrubThreads, P = kFastScrubPer, cps = 1;
-        fast_shape_for(n, true, &T, &P, &cps);
-        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)T * P * 32);
-        const int grid = e->sm_count * cps;
-#define CCM_SCRUB_SHAPE(TT, PP) \
-        if (T == TT && P == PP) err = launch_fast(scrub_st256_fast_kernel<TT, PP, kPolDefault>, grid, TT, st, s, nchunks, e->scrub_ctl(), zero_on_exit); else
-        CCM_SCRUB_SHAPE(512, 8) CCM_SCRUB_SHAPE(512, 4) CCM_SCRUB_SHAPE(256, 8) CCM_SCRUB_SHAPE(1024, 4) CCM_SCRUB_SHAPE(256, 4)
-        { set_error("no scrub instantiation for %dx%d", T, P); return CCM_ERR_INVALID; }
-#undef CCM_SCRUB_SHAPE
+        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)kFastScrubThreads * kFastScrubPer * 32);
+        err = launch_fast(CCM_FAST_SCRUB, e->sm_count, kFastScrubThreads, st, s, nchunks, e->scrub_ctl(), zero_on_exit);
         g_launches++;
         break;
       }
@@ -496,15 +479,8 @@ static int verify_range(ScrubEngine* e, const void* p, uint64_t n, int variant, 
       if (cfg == nullptr) {
         // library default: 148 persistent CTAs x 1024 threads, 4 x LDG.256 in flight per thread
         // per 128 KiB grab — verify_ld256_fast_kernel
-        int T = kFastVerifyThreads, P = kFastVerifyPer, cps = 1;
-        fast_shape_for(n, false, &T, &P, &cps);
-        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)T * P * 32);
-        const int grid = e->sm_count * cps;
-#define CCM_VERIFY_SHAPE(TT, PP) \
-        if (T == TT && P == PP) err = launch_fast(verify_ld256_fast_kernel<TT, PP, kPolStreaming>, grid, TT, st, s, nchunks, e->verify_ctl(), e->d_counter); else
-        CCM_VERIFY_SHAPE(1024, 4) CCM_VERIFY_SHAPE(1024, 2) CCM_VERIFY_SHAPE(512, 4) CCM_VERIFY_SHAPE(512, 8) CCM_VERIFY_SHAPE(256, 8)
-        { set_error("no verify instantiation for %dx%d", T, P); return CCM_ERR_INVALID; }
-#undef CCM_VERIFY_SHAPE
+        const uint64_t nchunks = s.body_vecs * 32 / ((uint64_t)kFastVerifyThreads * kFastVerifyPer * 32);
+        err = launch_fast(CCM_FAST_VERIFY, e->sm_count, kFastVerifyThreads, st, s, nchunks, e->verify_ctl(), e->d_counter);
         break;
       }
       Sched sc;

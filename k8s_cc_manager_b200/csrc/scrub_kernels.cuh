@@ -514,7 +514,12 @@ verify_ld256_fast_kernel(RegionSplit s, uint64_t nchunks, GrabCtl ctl, unsigned 
     if (c >= nchunks) break;
     unsigned long long nxt = 0;
     if (threadIdx.x == 0) nxt = atomicAdd(ctl.grab, 1ull);
-    const uint8_t* p = body + c * kChunk + threadIdx.x * 32u;
+    // DESCENDING chunk order.  The scrub ran in ascending order and left the ~126 MB it wrote last
+    // dirty in L2.  Reading upwards would stream the whole region from DRAM and, on top of that, evict
+    // those dirty lines (extra write-back traffic = +17 us per launch at any size: 157 vs 140 us at
+    // 1 GB, profiles/r2_small_region_shapes.log); reading downwards takes them out of L2 first, so the
+    // DRAM traffic of a read-back is R again, not R + L2.
+    const uint8_t* p = body + (nchunks - 1 - c) * kChunk + threadIdx.x * 32u;
     Vec32 v[PER_THREAD];
 #pragma unroll
     for (int u = 0; u < PER_THREAD; ++u) v[u] = ld32<POL>(p + (uint32_t)u * THREADS * 32u);  // all loads first
