@@ -125,3 +125,68 @@ def test_root_shims_expose_reference_names():
     for name in ("CCManager", "main", "create_readiness_file", "is_host_cc_enabled", "CC_MODE_CONFIG_LABEL",
                  "READINESS_FILE"):
         assert hasattr(entry, name), name
+
+
+def test_manager_recovers_from_a_crash_between_evict_and_reschedule(cluster, monkeypatch):
+    """SURVEY §8f N1 end to end on the fake API: the manager dies after the components were paused and
+    before they were restored (the reference loses the original values here: main.py:556-576 keeps them
+    in a local variable).  The next start finds the journal, restores the labels, and only then reconciles."""
+    import kubernetes
+    from kubernetes.watch import WatchScriptExhausted
+    from helpers import build_native_world
+    from k8s_cc_manager_b200 import drain_gate as G, manager
+    original = dict(SC.all_true_labels(), **{"nvidia.com/gpu.deploy.vgpu-manager": "custom", "nvidia.com/cc.mode": "on"})
+    build_native_world(SC.scenario("crash", gpus_=SC.gpus(4), modes=[]))
+    cluster.add_node(SC.NODE, original)
+    monkeypatch.setenv("EVICT_OPERATOR_COMPONENTS", "true")
+    monkeypatch.setenv("CC_JOURNAL_COMPONENT_LABELS", "true")
+    monkeypatch.setattr(G, "_now", cluster.clock.time)
+    monkeypatch.setattr(G, "_pause", cluster.clock.sleep)
+
+    class Died(BaseException):
+        pass
+
+    mgr = manager.CCManager(SC.NODE, "on", True, scrub_mode="skip")
+
+    def die(*a, **k):
+        raise Died()                                       # SIGKILL stand-in: no except/finally of ours runs after it
+    monkeypatch.setattr(mgr, "_set_cc_mode_direct", die)
+    with pytest.raises(Died):
+        mgr.set_cc_mode("on")
+    paused = cluster.labels(SC.NODE)
+    assert paused["nvidia.com/gpu.deploy.vfio-manager"] == G.PAUSED_STR
+    assert paused["nvidia.com/gpu.deploy.vgpu-manager"] == "custom_" + G.PAUSED_STR
+    assert G.JOURNAL_ANNOTATION in cluster.nodes[SC.NODE].metadata.annotations
+
+    # ---- restart ------------------------------------------------------------------------------
+    mgr2 = manager.CCManager(SC.NODE, "on", True, scrub_mode="skip")
+    seen_at_reconcile = {}
+    real = mgr2.set_cc_mode
+
+    def spy(mode):
+        seen_at_reconcile.update(cluster.labels(SC.NODE))
+        return real(mode)
+    mgr2.set_cc_mode = spy
+    monkeypatch.setattr(manager, "create_readiness_file", lambda: None)
+    with pytest.raises(WatchScriptExhausted):
+        mgr2.watch_and_apply()
+    # the labels were back to their ORIGINAL values before the reconcile touched anything
+    assert {k: seen_at_reconcile[k] for k in G.COMPONENT_LABELS} == {k: original[k] for k in G.COMPONENT_LABELS}
+    final = cluster.labels(SC.NODE)
+    assert {k: final[k] for k in G.COMPONENT_LABELS} == {k: original[k] for k in G.COMPONENT_LABELS}
+    assert final["nvidia.com/cc.mode.state"] == "on"
+    assert G.JOURNAL_ANNOTATION not in (cluster.nodes[SC.NODE].metadata.annotations or {})
+    assert G.recover_journaled_labels(kubernetes.client.CoreV1Api(), SC.NODE) is None
+
+    # without the journal (reference behaviour) the same crash leaves the components paused for good
+    cluster2 = kubernetes.reset_cluster()
+    cluster2.add_node(SC.NODE, original)
+    build_native_world(SC.scenario("crash", gpus_=SC.gpus(4), modes=[]))
+    monkeypatch.setenv("CC_JOURNAL_COMPONENT_LABELS", "false")
+    mgr3 = manager.CCManager(SC.NODE, "on", True, scrub_mode="skip")
+    monkeypatch.setattr(mgr3, "_set_cc_mode_direct", die)
+    with pytest.raises(Died):
+        mgr3.set_cc_mode("on")
+    mgr4 = manager.CCManager(SC.NODE, "on", True, scrub_mode="skip")
+    assert mgr4.recover_interrupted_transition() is False
+    assert cluster2.labels(SC.NODE)["nvidia.com/gpu.deploy.vfio-manager"] == G.PAUSED_STR

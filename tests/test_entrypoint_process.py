@@ -76,3 +76,37 @@ def test_entrypoint_scrub_gate_fails_closed_without_cuda(tmp_path):
     assert result["labels"]["nvidia.com/cc.mode.state"] == "failed"
     assert result["labels"]["nvidia.com/gpu.deploy.vfio-manager"] == "true"
     assert "no CUDA device" in proc.stderr or "HBM scrub" in proc.stderr
+
+
+def test_entrypoint_refuses_a_simulated_register_backend_unless_told(tmp_path):
+    """with nothing configured libccm picks sim/cudasim and the manager would publish
+    cc.mode.state=on without touching hardware.  The production entrypoint must refuse."""
+    proc = run(["--node-name", "node-a"], {"CCM_ALLOW_SIM": "0", "CC_SCRUB_MODE": "skip"}, tmp_path)
+    assert proc.returncode == 1
+    assert "SIMULATED register backend" in proc.stderr and "CCM_ALLOW_SIM=1" in proc.stderr
+    assert "RESULT" not in proc.stdout                       # nothing was labelled, nothing was staged
+    proc = run(["--node-name", "node-a"], {"CCM_ALLOW_SIM": "1", "CC_SCRUB_MODE": "skip"}, tmp_path)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+
+
+def test_entrypoint_prefers_gpu_admin_tools_when_the_image_ships_it(tmp_path, monkeypatch):
+    """Unset CC_DEVICE_LIBRARY: <app dir>/gpu-admin-tools (reference main.py:30-31) wins over libccm's registers."""
+    from k8s_cc_manager_b200 import manager
+    tools = tmp_path / "gpu-admin-tools" / "pci"
+    tools.mkdir(parents=True)
+    (tools / "__init__.py").write_text("")
+    (tools / "devices.py").write_text("def find_gpus():\n    return [], 0\n")
+    monkeypatch.setenv("GPU_ADMIN_TOOLS_PATH", str(tmp_path / "gpu-admin-tools"))
+    monkeypatch.delenv("CC_DEVICE_LIBRARY", raising=False)
+    import sys as _sys
+    for m in ("pci", "pci.devices"):
+        _sys.modules.pop(m, None)
+    try:
+        source = manager._device_source_from_env()
+        assert source is not None and source() == ([], 0)    # the foreign find_gpus, wrapped with the scrub
+    finally:
+        for m in ("pci", "pci.devices"):
+            _sys.modules.pop(m, None)
+        _sys.path.remove(str(tmp_path / "gpu-admin-tools"))
+    monkeypatch.setenv("CC_DEVICE_LIBRARY", "libccm")
+    assert manager._device_source_from_env() is None         # CCM_ALLOW_SIM=1 in the test environment
