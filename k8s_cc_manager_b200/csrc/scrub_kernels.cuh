@@ -270,19 +270,22 @@ scrub_st256_fast_kernel(RegionSplit s, uint64_t nchunks, GrabCtl ctl, unsigned l
   uint8_t* body = s.base + s.head;
   __shared__ unsigned long long s_chunk[2];
   pdl_wait();
-  // The FIRST chunk of a CTA is static (its block index): the first stores go out without waiting
-  // for an atomic round trip; grabbed indices continue after the gridDim.x static ones.
-  uint64_t c = blockIdx.x;
+  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(ctl.grab, 1ull);
+  __syncthreads();
   int buf = 0;
-  while (c < nchunks) {
+  for (;;) {
+    const uint64_t c = s_chunk[buf];
+    if (c >= nchunks) break;
     unsigned long long nxt = 0;
-    if (threadIdx.x == 0) nxt = atomicAdd(ctl.grab, 1ull) + gridDim.x;  // next grab in flight while we store
+    // next grab in flight while we store.  The raw result goes straight to shared memory at the end of
+    // the iteration: any arithmetic on it here makes warp 0 wait out the ~1 us atomic before its stores
+    // (a "static first chunk + offset" variant lost 10 % of the read-back rate that way, r2h).
+    if (threadIdx.x == 0) nxt = atomicAdd(ctl.grab, 1ull);
     uint8_t* p = body + c * kChunk + threadIdx.x * 32u;
 #pragma unroll
     for (int u = 0; u < PER_THREAD; ++u) st_zero32<POL>(p + (uint32_t)u * THREADS * 32u);
-    if (threadIdx.x == 0) s_chunk[buf] = nxt;
+    if (threadIdx.x == 0) s_chunk[buf ^ 1] = nxt;
     __syncthreads();
-    c = s_chunk[buf];
     buf ^= 1;  // two slots: a slow warp may still be reading slot k when thread 0 already writes slot k+1
   }
   pdl_launch_dependents();
@@ -506,11 +509,14 @@ verify_ld256_fast_kernel(RegionSplit s, uint64_t nchunks, GrabCtl ctl, unsigned 
   uint64_t cnt = 0;
   __shared__ unsigned long long s_chunk[2];
   pdl_wait();
-  uint64_t c = blockIdx.x;  // static first chunk, grabbed ones follow (see the scrub kernel)
+  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(ctl.grab, 1ull);
+  __syncthreads();
   int buf = 0;
-  while (c < nchunks) {
+  for (;;) {
+    const uint64_t c = s_chunk[buf];
+    if (c >= nchunks) break;
     unsigned long long nxt = 0;
-    if (threadIdx.x == 0) nxt = atomicAdd(ctl.grab, 1ull) + gridDim.x;
+    if (threadIdx.x == 0) nxt = atomicAdd(ctl.grab, 1ull);
     // DESCENDING chunk order.  The scrub ran in ascending order and left the ~126 MB it wrote last
     // dirty in L2.  Reading upwards would stream the whole region from DRAM and, on top of that, evict
     // those dirty lines (extra write-back traffic = +17 us per launch at any size: 157 vs 140 us at
@@ -533,9 +539,8 @@ verify_ld256_fast_kernel(RegionSplit s, uint64_t nchunks, GrabCtl ctl, unsigned 
         for (int k = 0; k < 8; ++k) n += nonzero_bytes_in_word(v[u].w[k]);
       cnt += n;
     }
-    if (threadIdx.x == 0) s_chunk[buf] = nxt;
+    if (threadIdx.x == 0) s_chunk[buf ^ 1] = nxt;
     __syncthreads();
-    c = s_chunk[buf];
     buf ^= 1;
   }
   pdl_launch_dependents();
