@@ -99,3 +99,65 @@ def test_entrypoint_selects_foreign_library(foreign, monkeypatch):
     monkeypatch.setenv("CC_DEVICE_LIBRARY", "other")
     with pytest.raises(ValueError):
         manager._device_source_from_env()
+
+
+# --------------------------------------------------------------------------------------------------
+# a8, the deliverable that IS possible without hardware: the product, configured the way a real CC node
+# runs it (CC_DEVICE_LIBRARY=gpu-admin-tools -> every register op is DELEGATED to the foreign library,
+# libccm only adds the scrub), must drive that library through exactly the call transcript the
+# unmodified reference produced on the same library for the same scenario (tests/golden/transitions.json,
+# recorded by oracle/gen_golden.py).  Same ops, same order, same arguments, same end registers, same
+# labels and return values — for all 31 scenarios, faults and PPCIe included.
+import json as _json
+
+_GOLDEN = {s["name"]: s for s in _json.loads(
+    (Path(__file__).parent / "golden" / "transitions.json").read_text())["scenarios"]}
+
+
+@pytest.mark.parametrize("name", sorted(_GOLDEN))
+def test_delegating_adapter_replays_the_reference_call_transcript(name, foreign, monkeypatch):
+    import os
+    import kubernetes  # noqa: F401
+    from helpers import build_cluster
+    from k8s_cc_manager_b200 import drain_gate, manager
+    w, _find = foreign
+    sc = {s["name"]: s for s in SC.transition_scenarios()}[name]
+    exc_types = {"GpuError": sys.modules["_state"].GpuError, "RuntimeError": RuntimeError}
+    for g in sc["gpus"]:
+        d = w.add_gpu(g["bdf"], cc=g["cc"], ppcie=g["ppcie"], cc_supported=g["cc_supported"],
+                      ppcie_supported=g["ppcie_supported"])
+        d.stuck = g["stuck"]
+        d.fail = {op: exc_types[t](f"injected {op} failure on {g['bdf']}") for op, t in g["fail"].items()}
+    for s in sc["switches"]:
+        d = w.add_nvswitch(s["bdf"], ppcie=s["ppcie"], ppcie_supported=s["ppcie_supported"])
+        d.stuck = s["stuck"]
+        d.fail = {op: exc_types[t](f"injected {op} failure on {s['bdf']}") for op, t in s["fail"].items()}
+    build_native_world(SC.scenario("p", gpus_=SC.gpus(max(1, len(sc["gpus"]))), modes=[]))   # libccm side: no CUDA
+    c = build_cluster(sc)
+    monkeypatch.setenv("EVICT_OPERATOR_COMPONENTS", "true" if sc["evict"] else "false")
+    monkeypatch.setenv("OPERATOR_NAMESPACE", SC.NAMESPACE)
+    monkeypatch.setenv("CC_DEVICE_LIBRARY", "gpu-admin-tools")
+    monkeypatch.setenv("GPU_ADMIN_TOOLS_PATH", str(FAKE))
+    monkeypatch.setattr(drain_gate, "_now", c.clock.time)
+    monkeypatch.setattr(drain_gate, "_pause", c.clock.sleep)
+    source = manager._device_source_from_env()            # the production wiring, not a hand-made lambda
+    assert source is not None
+    if str(FAKE) in sys.path[1:]:
+        sys.path.remove(str(FAKE))                        # _device_source_from_env prepends it once more
+    mgr = manager.CCManager(SC.NODE, "on", sc["host_cc"], device_source=source, max_parallel=1, scrub_mode="skip")
+    want = _GOLDEN[name]
+    for i, mode in enumerate(sc["modes"]):
+        n_dev = len(w.trace)
+        got = {}
+        try:
+            got["result"] = mgr.set_cc_mode(mode)
+        except SystemExit as exc:
+            got["exit"] = exc.code
+        w_step = want["steps"][i]
+        assert w.trace_lines()[n_dev:] == w_step["device_trace"], f"{name} step {i}: foreign call transcript"
+        assert got.get("result") == w_step.get("result") and got.get("exit") == w_step.get("exit")
+        assert {d.bdf: {"cc": d.cc_mode, "ppcie": d.ppcie_mode} for d in w.devices} == w_step["registers"]
+        assert c.labels(SC.NODE) == w_step["labels"]
+        if "exit" in got:
+            break
+    assert os.environ["CC_DEVICE_LIBRARY"] == "gpu-admin-tools"
