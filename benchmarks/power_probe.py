@@ -40,7 +40,7 @@ idle = [pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0 for _ in range(10)]
 out["idle_w"] = statistics.median(idle)
 for name, v in (("scrub_st256", N.SCRUB_ST256), ("scrub_tma", N.SCRUB_TMA), ("scrub_st128", N.SCRUB_ST128), ("scrub_memset", N.SCRUB_MEMSET)):
     run(name, lambda ms, v=v: L.ccm_arena_scrub(0, v, None, None, C.byref(ms)))
-for name, v in (("verify_ld256", N.VERIFY_LD256), ("verify_tma", N.VERIFY_TMA), ("verify_ld128", N.VERIFY_LD128)):
+for name, v in (("verify_ld256", N.VERIFY_LD256), ("verify_ld128", N.VERIFY_LD128)):
     run(name, lambda ms, v=v: L.ccm_arena_verify(0, v, None, None, C.byref(nz), C.byref(ms)))
 L.ccm_arena_release(0)
 Path("gpurun_out").mkdir(exist_ok=True)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-1 experiment: verify kernel shapes with the dynamic schedule (64 GiB region)
-S="ld256,vtma"
+S="ld256"
 for cps in 1 2 4 8; do for th in 128 256 512 1024; do
   if [ $((cps*th)) -gt 2048 ] || [ $((cps*th)) -lt 512 ]; then continue; fi
   for un in 2 4 8; do

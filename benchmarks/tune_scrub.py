@@ -135,9 +135,71 @@ def main():
     ms, nz = time_verify(L, dev, N.VERIFY_LD128, None, 1)
     assert nz == R, (nz, R)
     rec("verify_dirty", "ld128", None, ms)
-    ms, nz = time_verify(L, dev, N.VERIFY_TMA, None, 1)
+    check(L.ccm_arena_scrub(dev, N.SCRUB_AUTO, None, None, None), "scrub")
+
+    for vname, v in (("ld256", N.VERIFY_LD256), ("ld128", N.VERIFY_LD128)):
+        for cps, th, un, pol in itertools.product([1, 2, 4, 8], [128, 256, 512, 1024], [1, 2, 4, 8], [1, 2, 3]):
+            if cps * th > 2048 or cps * th < 256:
+                continue
+            if vname == "ld256" and un == 8 and th * cps > 1024:
+                continue  # register budget: 64 regs of payload per thread
+            if args.quick and (un not in (2, 4) or th not in (256, 512)):
+                continue
+            cfg = N.launch_cfg(cps, th, 0, un, pol)
+            ms, nz = time_verify(L, dev, v, cfg, args.reps)
+            assert nz == 0, (vname, cps, th, un, pol, nz)
+            rec("verify", vname, cfg, ms)
+    check(L.ccm_arena_release(dev), "release")
+    out["max_arena"]["ms_release"] = (time.perf_counter() - t2) * 1e3
+    print(f"release {out['max_arena']['ms_release']:.1f} ms", flush=True)
+
+    # ---- sweep region
+    want = int(args.gib * 2**30) if args.gib > 0 else 0
+    check(L.ccm_arena_acquire(dev, want, C.byref(ai)), "acquire sweep")
+    R = ai.bytes
+    out["sweep_bytes"] = R
+    print(f"sweep region {R/2**30:.1f} GiB", flush=True)
+
+    def rec(kind, variant, cfg, ms, extra=None):
+        row = {"kind": kind, "variant": variant, "ctas_per_sm": cfg.ctas_per_sm if cfg else 0,
+               "threads": cfg.threads_per_cta if cfg else 0, "unroll": cfg.unroll if cfg else 0,
+               "policy": cfg.cache_policy if cfg else 0, "tile": cfg.tile_bytes if cfg else 0,
+               "ms": ms, "gbs": R / ms / 1e6}
+        if extra:
+            row.update(extra)
+        out["results"].append(row)
+        print(json.dumps(row), flush=True)
+
+    # library bar
+    rec("scrub", "memset", None, time_scrub(L, dev, N.SCRUB_MEMSET, None, args.reps))
+
+    pol_all = [1, 2, 3] if not args.quick else [1]
+    # ST variants
+    for vname, v in (("st256", N.SCRUB_ST256), ("st128", N.SCRUB_ST128)):
+        combos = itertools.product([1, 2, 4, 8], [128, 256, 512, 1024], [1, 2, 4, 8], pol_all)
+        for cps, th, un, pol in combos:
+            if cps * th > 2048 or cps * th < 256:
+                continue
+            if args.quick and (un not in (2, 4) or th not in (256, 512)):
+                continue
+            cfg = N.launch_cfg(cps, th, 0, un, pol)
+            rec("scrub", vname, cfg, time_scrub(L, dev, v, cfg, args.reps))
+    # TMA
+    for cps, th, tile, grp, pol in itertools.product([1, 2, 4], [32, 128], [8192, 16384, 32768, 65536],
+                                                     [1, 4], [1, 2]):
+        if cps * tile > 200 * 1024:
+            continue
+        cfg = N.launch_cfg(cps, th, tile, grp, pol)
+        rec("scrub", "tma", cfg, time_scrub(L, dev, N.SCRUB_TMA, cfg, args.reps))
+
+    # verify: must count exactly on a dirty region too
+    check(L.ccm_arena_fill(dev, 0xA5, None), "fill")
+    ms, nz = time_verify(L, dev, N.VERIFY_LD256, None, 1)
     assert nz == R, (nz, R)
-    rec("verify_dirty", "tma", None, ms)
+    rec("verify_dirty", "ld256", None, ms)
+    ms, nz = time_verify(L, dev, N.VERIFY_LD128, None, 1)
+    assert nz == R, (nz, R)
+    rec("verify_dirty", "ld128", None, ms)
     check(L.ccm_arena_scrub(dev, N.SCRUB_AUTO, None, None, None), "scrub")
 
     for vname, v in (("ld256", N.VERIFY_LD256), ("ld128", N.VERIFY_LD128)):
