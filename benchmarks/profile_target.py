@@ -35,6 +35,7 @@ def main():
     assert rc == 0, N.last_error()
     ms = C.c_float()
     nz = C.c_uint64()
+    print(f"arena {ai.bytes} bytes in {ai.segments} segment(s)", flush=True)
     for item in args.seq.split(","):
         parts = item.split(":")
         name = parts[0]
