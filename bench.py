@@ -597,15 +597,17 @@ def node_leg(args):
     clean = all(r.clean for r in reports)
     cov = [r.coverage for r in reports]
     victim = gpus[-1]
-    L.ccm_sim_set(victim.index, b"scrub_inject", 5)
+    # 3 bytes: first, an unaligned and the middle byte of the first chunk — valid for both launch shapes of the
+    # product call (pipelined: 4 candidates per chunk; mapped-first, which n > 1 uses: 4 for the whole range)
+    L.ccm_sim_set(victim.index, b"scrub_inject", 3)
     drill, _ = D.scrub_and_verify_many(gpus, 2 << 30)
     L.ccm_sim_set(victim.index, b"scrub_inject", 0)
-    drill_ok = all((r.status == N.ERR_DIRTY and r.nonzero_bytes == 5) if r.bdf == victim.bdf else r.clean for r in drill)
+    drill_ok = all((r.status == N.ERR_DIRTY and r.nonzero_bytes == 3) if r.bdf == victim.bdf else r.clean for r in drill)
     out["node_checks"] = {
         "gpus": n, "all_clean": clean, "coverage_min": min(cov), "coverage_max": max(cov),
         "bytes_unreached_max": max(r.bytes_unreached for r in reports),
         "first_gate_incl_context_creation_ms": (time.perf_counter() - t0) * 1e3, "first_gate_wall_ms": wall_ms,
-        "dirt_drill": {"victim": victim.bdf, "injected": 5, "statuses": [r.status for r in drill],
+        "dirt_drill": {"victim": victim.bdf, "injected": 3, "statuses": [r.status for r in drill],
                        "victim_counted": [r.nonzero_bytes for r in drill if r.bdf == victim.bdf][0], "ok": drill_ok},
         "ok": bool(clean and min(cov) >= 0.99 and drill_ok)}
     for g in gpus:
