@@ -153,6 +153,7 @@ class CCManager:
         self._sleep = time.sleep
         self._pool: Optional[ThreadPoolExecutor] = None
         self._pool_size = 0
+        self._gate_gpus: list = []      # GPUs whose gate resources (HBM on its way back, CUDA contexts) are still held
         self.last_transition: dict = {}
 
         if v1 is not None:
@@ -446,6 +447,16 @@ class CCManager:
         self._run_scrub(gpus)
 
     @staticmethod
+    def _native_of(gpu):
+        """The libccm device that scrubs `gpu`: the device itself, or the one a ScrubbingProxy found by PCI
+        address behind a foreign register library; None for anything else."""
+        if isinstance(gpu, _devices.NvidiaDevice):
+            return gpu
+        if isinstance(gpu, _devices.ScrubbingProxy):
+            return object.__getattribute__(gpu, "_native")
+        return None
+
+    @staticmethod
     def _can_scrub(gpu) -> bool:
         if isinstance(gpu, _devices.ScrubbingProxy):
             return object.__getattribute__(gpu, "_native") is not None
@@ -464,7 +475,7 @@ class CCManager:
         CC_RELEASE_CUDA_CONTEXT=true (default), resets each GPU's CUDA primary context — all GPUs
         at once (one native thread each).  Runs after the state label is out, so the driver's
         unmap/release/teardown work overlaps the API round trips instead of delaying the verdict."""
-        gpus, self._gate_gpus = getattr(self, "_gate_gpus", []), []
+        gpus, self._gate_gpus = self._gate_gpus, []
         if not gpus:
             return
         started = time.perf_counter()
@@ -476,8 +487,8 @@ class CCManager:
                 logger.warning("Could not %s: %s", what, exc)
 
         in_process = self.scrub_isolation != "process"   # a worker process took its contexts with it
-        native = [g for g in gpus if isinstance(g, _devices.NvidiaDevice)]
-        others = [g for g in gpus if not isinstance(g, _devices.NvidiaDevice)]
+        native = [n for n in map(self._native_of, gpus) if n is not None]      # libccm devices, also behind proxies
+        others = [g for g in gpus if self._native_of(g) is None]
         if self.release_cuda_context:
             if native and in_process:
                 attempt("release the CUDA contexts", lambda: _devices.release_cuda_contexts(native))
@@ -518,8 +529,12 @@ class CCManager:
         started = time.perf_counter()
         if self.scrub_isolation == "process":
             reports = self._scrub_in_worker_process(gpus)
-        elif all(isinstance(g, _devices.NvidiaDevice) for g in gpus) and self._workers(len(gpus)) == len(gpus):
-            reports, _ = _devices.scrub_and_verify_many(gpus, self.scrub_bytes)
+        elif all(self._native_of(g) is not None for g in gpus) and self._workers(len(gpus)) == len(gpus):
+            # ONE native call for the whole node (maps first, then launches: DESIGN.md §6) — also when the
+            # register work belongs to a foreign library and libccm only scrubs (ScrubbingProxy)
+            reports, _ = _devices.scrub_and_verify_many([self._native_of(g) for g in gpus], self.scrub_bytes)
+            for rep, gpu in zip(reports, gpus):
+                rep.bdf = gpu.bdf
         else:
             def one(gpu):
                 if not hasattr(gpu, "scrub_and_verify"):

@@ -20,7 +20,7 @@ def test_referenced_paths_exist(doc):
         candidates = []
         if token.startswith(PREFIXES):
             candidates.append(token)
-        elif doc.startswith("profiles/") and re.fullmatch(r"r1[a-z]?_[\w.{},-]+\.(json|csv|log|txt|md)", token):
+        elif doc.startswith("profiles/") and re.fullmatch(r"r[12][a-z]?_[\w.{},-]+\.(json|csv|log|txt|md)", token):
             candidates.append("profiles/" + token)
         elif doc.startswith("benchmarks/") and re.fullmatch(r"[\w-]+\.(py|sh|cu)", token):
             candidates.append("benchmarks/" + token)
