@@ -636,10 +636,6 @@ def node_leg(args):
         if not args.no_transition:
             # LAST: this policy resets the CUDA primary contexts (torch, used by B2 above, is dead afterwards)
             out["transition"]["daemon_default_release_contexts"] = measure_transitions(L, N, n, release_contexts=True)
-            if os.environ.get("BENCH_CTX_AB") == "1":   # builder's A/B: contexts created / reset one at a time
-                os.environ["CCM_CTX_SERIAL"] = "1"
-                out["transition"]["ab_release_contexts_ctx_serial"] = measure_transitions(L, N, n, release_contexts=True)
-                del os.environ["CCM_CTX_SERIAL"]
             out["transition"]["simulated"] = ["CC mode registers (cudasim backend; the box's driver-bound GPUs cannot be reset)",
                                              "reset/boot latency = 0 ms", "kubernetes API (in-memory fake, 0 ms RTT)"]
             out["transition"]["real"] = ["full-HBM scrub-and-verify gate on every GPU", "CUDA context creation / reset",

