@@ -511,7 +511,7 @@ def run_ours(args):
         line["e2e_host_buffers"] = host_rt
     if not args.no_node_leg:
         node = run_node_leg(world, args)
-        for key in ("node_checks", "transition", "baselines"):
+        for key in ("node_checks", "node_gate", "transition", "baselines"):
             if key in node:
                 if key == "node_checks":
                     line["checks"]["node"] = node[key]
@@ -556,7 +556,9 @@ def run_node_leg(n_gpus, args):
     env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "CCM_ARENA_RESERVE_MB"):
         env.pop(k, None)
-    cmd = [sys.executable, str(ROOT / "bench.py"), "--node-leg", "--gpus", str(n_gpus)]
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--node-leg", "--gpus", str(n_gpus),
+           "--node-gate-calls", str(args.node_gate_calls), "--fresh-context-calls", str(args.fresh_context_calls),
+           "--b1-sample-gib", str(args.b1_sample_gib)]
     if args.no_transition:
         cmd.append("--no-transition")
     if args.no_baselines:
@@ -623,9 +625,26 @@ def node_leg(args):
             g.wait_scrub_released()
         c.append(time.perf_counter() - t0)
         assert all(r.clean for r in reps)
-    out["node_checks"]["concurrent_gate_one_process"] = {
+    out["node_gate"] = {"gpus": n, "launcher": "ONE process, one thread per GPU (ccm_scrub_verify_many; maps first when N > 1)"}
+    out["node_gate"]["warm_contexts"] = {
         "verdict_s": stats(v), "cycle_s": stats(c), "bytes_total": sum(r.bytes_scrubbed for r in reps),
         "acquire_host_ms_max": max(r.ms_acquire for r in reps), "gpu_span_ms_max": max(r.ms_gpu_span for r in reps)}
+
+    # ---- the same gate on FRESH contexts: what a daemon that drops its contexts after every gate (the default)
+    # pays before the first byte is scrubbed — context creation is part of the time to the verdict --------------
+    fv, fc = [], []
+    for _ in range(args.fresh_context_calls):
+        D.release_cuda_contexts(gpus)                                  # untimed: contexts gone, HBM back
+        t0 = time.perf_counter()
+        reps, _ = D.scrub_and_verify_many(gpus, 0)                     # creates N primary contexts, then the gate
+        fv.append(time.perf_counter() - t0)
+        assert all(r.clean for r in reps)
+        D.release_cuda_contexts(gpus)                                  # joins the HBM give-back, resets the contexts
+        fc.append(time.perf_counter() - t0)
+    if fv:
+        out["node_gate"]["fresh_contexts"] = {
+            "verdict_s": stats(fv), "cycle_incl_context_reset_s": stats(fc),
+            "what": "per call: N primary contexts created + full-HBM gate (verdict), then HBM handed back + contexts reset"}
 
     logging.disable(logging.CRITICAL)
     try:
@@ -863,6 +882,7 @@ def main():
     ap.add_argument("--cpu-passes", type=int, default=40)
     ap.add_argument("--b1-sample-gib", type=float, default=2.0)
     ap.add_argument("--node-gate-calls", type=int, default=7)
+    ap.add_argument("--fresh-context-calls", type=int, default=4)
     ap.add_argument("--node-leg-timeout-s", type=float, default=600.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-transition", action="store_true")
