@@ -214,14 +214,6 @@ def main():
             ms, nz = time_verify(L, dev, v, cfg, args.reps)
             assert nz == 0, (vname, cps, th, un, pol, nz)
             rec("verify", vname, cfg, ms)
-    for cps, th, tile in itertools.product([1, 2, 3], [160, 288, 544], [8192, 16384, 32768]):
-        if cps * tile * 4 > 200 * 1024:
-            continue
-        cfg = N.launch_cfg(cps, th, tile, 0, 0)
-        ms, nz = time_verify(L, dev, N.VERIFY_TMA, cfg, args.reps)
-        assert nz == 0, ("tma", cps, th, tile, nz)
-        rec("verify", "tma", cfg, ms)
-
     check(L.ccm_arena_release(dev), "release")
 
     for kind in ("scrub", "verify"):
