@@ -496,8 +496,10 @@ int ccm_scrub_verify(int dev, uint64_t bytes, ccm_scrub_result* out) { return sc
 int ccm_scrub_release_wait(int dev, double* ms_release, double* ms_waited) {
   if (ms_release) *ms_release = 0;
   if (ms_waited) *ms_waited = 0;
-  int rc; ScrubEngine* e = engine_of_dev(dev, &rc);
-  return e ? engine_release_wait(e, ms_release, ms_waited) : rc;
+  const int ord = cuda_ordinal_of(dev);
+  if (ord < 0) return ord;
+  ScrubEngine* e = engine_lookup(ord);  // no engine (or a torn-down one): nothing can be pending — and asking
+  return e ? engine_release_wait(e, ms_release, ms_waited) : (int)CCM_OK;  // must not re-create a CUDA context
 }
 
 int ccm_scrub_verify_many(int n, const int* devs, uint64_t bytes, ccm_scrub_result* out, double* wall_ms) {

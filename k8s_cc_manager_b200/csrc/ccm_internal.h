@@ -21,6 +21,7 @@ int cuda_describe(int ordinal, char* bdf, size_t bdf_cap, char* name, size_t nam
 
 struct ScrubEngine;  // one per CUDA ordinal, created lazily
 ScrubEngine* engine_for(int ordinal);  // nullptr + error text if unusable
+ScrubEngine* engine_lookup(int ordinal);  // the engine if it exists; never creates a context
 
 int engine_arena_acquire(ScrubEngine*, uint64_t bytes, ccm_arena_info* out);
 int engine_arena_release(ScrubEngine*, double* ms);

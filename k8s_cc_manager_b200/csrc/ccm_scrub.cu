@@ -102,7 +102,6 @@ struct ScrubEngine {
   // joined by whoever needs the memory (or the context) next
   std::thread reaper;
   double reaper_ms = 0;        // duration of the last background release
-  bool reaper_failed = false;
 
   ~ScrubEngine() { if (reaper.joinable()) reaper.join(); }
 
@@ -185,6 +184,13 @@ ScrubEngine* engine_for(int ordinal) {
   std::lock_guard<std::mutex> g(e->mu);
   if (e->init() != CCM_OK) return nullptr;
   return e;
+}
+
+// The engine of an ordinal if one was ever created — WITHOUT (re)creating a CUDA context for it.
+ScrubEngine* engine_lookup(int ordinal) {
+  std::lock_guard<std::mutex> g(g_engines_mu);
+  if (ordinal < 0 || (size_t)ordinal >= g_engines.size()) return nullptr;
+  return g_engines[ordinal].get();
 }
 
 // Every engine_* entry point calls this right after taking e->mu: a concurrent
@@ -874,7 +880,7 @@ static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t injec
   acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
   int rc = CCM_OK;
   double host_acquire = 0;
-  int timed = 0;  // chunks with an event triple
+  int timed = 0;  // chunks with an event triple (the first kMaxPipeChunks; a badly fragmented HBM may produce more)
 
   // enqueue scrub (+ read-back) of [off, off+n) with CUDA events around each kernel
   auto enqueue = [&](uint64_t off, uint64_t n) -> int {
@@ -979,7 +985,6 @@ static int scrub_verify_pipelined(ScrubEngine* e, uint64_t bytes, uint64_t injec
   if (rc == CCM_OK && async_release_enabled()) {
     r->release_deferred = 1;
     r->ms_release = 0;
-    e->reaper_failed = false;
     const int ordinal = e->ordinal;
     e->reaper = std::thread([e, ordinal, mm = std::move(m)]() mutable {
       cudaSetDevice(ordinal);

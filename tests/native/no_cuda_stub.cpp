@@ -7,6 +7,7 @@ namespace ccm {
 int cuda_device_count() { return 0; }
 int cuda_describe(int, char*, size_t, char*, size_t, uint64_t*) { return CCM_ERR_NO_CUDA; }
 ScrubEngine* engine_for(int) { set_error("stub build: no CUDA"); return nullptr; }
+ScrubEngine* engine_lookup(int) { return nullptr; }
 int engine_arena_acquire(ScrubEngine*, uint64_t, ccm_arena_info*) { return CCM_ERR_NO_CUDA; }
 int engine_arena_release(ScrubEngine*, double*) { return CCM_ERR_NO_CUDA; }
 int engine_arena_scrub(ScrubEngine*, int, const ccm_launch_cfg*, void*, float*) { return CCM_ERR_NO_CUDA; }

@@ -81,6 +81,8 @@ t0 = time.perf_counter(); r1 = gpu.scrub_and_verify(4 << 30); out["first_call_s"
 out["holding"] = mine()
 gpu.release_cuda_context()
 out["after_release"] = mine()
+gpu.wait_scrub_released()                                   # asking must not bring the context back
+out["after_release_and_wait"] = mine()
 t0 = time.perf_counter(); r2 = gpu.scrub_and_verify(4 << 30); out["call_after_release_s"] = time.perf_counter() - t0
 t0 = time.perf_counter(); r3 = gpu.scrub_and_verify(4 << 30); out["warm_call_s"] = time.perf_counter() - t0
 out["clean"] = [r1.clean, r2.clean, r3.clean]
@@ -98,6 +100,7 @@ def test_release_drops_the_cuda_context_and_scrub_comes_back(tmp_path):
     out = json.loads(next(l for l in proc.stdout.splitlines() if l.startswith("RESULT "))[7:])
     assert out["before"] is False and out["holding"] is True
     assert out["after_release"] is False and out["after_second_release"] is False
+    assert out["after_release_and_wait"] is False
     assert out["clean"] == [True, True, True]
     print(f"\ncontext re-creation: first {out['first_call_s']*1e3:.0f} ms, after release "
           f"{out['call_after_release_s']*1e3:.0f} ms, warm {out['warm_call_s']*1e3:.0f} ms")
