@@ -4,6 +4,8 @@
   A  one process, one thread per GPU, pipelined (map chunk i+1 while chunk i is scrubbed/read back)
   B  one process, threads, CCM_MAP_FIRST=1 (map everything, then two launches)
   C  one process, threads, pipelined scrub but ONE verify at the end (CCM_INTERLEAVE_VERIFY=0)
+  F  one process, threads, COARSE pipeline: 64 GiB chunks (3 + tail instead of 23), CCM_MAP_FIRST=0
+  G  one process, threads, coarse pipeline: 32 GiB chunks
   D  one fresh worker process PER GPU (native ccm-scrub --bdf X), all started together
   E  one fresh worker process for all GPUs (threads inside)
 
@@ -68,11 +70,17 @@ def main():
                 os.environ.pop(k, None)
 
     if "A" in modes:
-        in_process("A in-process threads, pipelined + interleaved verify", {})
+        in_process("A in-process threads, pipelined + interleaved verify (23 chunks)", {"CCM_MAP_FIRST": "0"})
     if "B" in modes:
         in_process("B in-process threads, map first", {"CCM_MAP_FIRST": "1"})
     if "C" in modes:
         in_process("C in-process threads, pipelined scrub, one verify", {"CCM_INTERLEAVE_VERIFY": "0"})
+    if "F" in modes:
+        in_process("F in-process threads, coarse pipeline 64 GiB chunks",
+                   {"CCM_MAP_FIRST": "0", "CCM_VMM_FIRST_CHUNK_MB": "65536", "CCM_VMM_CHUNK_MB": "65536"})
+    if "G" in modes:
+        in_process("G in-process threads, coarse pipeline 32 GiB chunks",
+                   {"CCM_MAP_FIRST": "0", "CCM_VMM_FIRST_CHUNK_MB": "32768", "CCM_VMM_CHUNK_MB": "32768"})
     # contexts of THIS process must not sit on the GPUs while the workers measure "all free HBM"
     D.release_cuda_contexts(gpus)
     env = dict(os.environ, CCM_BACKEND="cudasim")
