@@ -63,3 +63,33 @@ def test_top_level_makefile_targets_exist():
     out = subprocess.run(["make", "-n", "native", "oracle"], cwd=ROOT, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert "k8s_cc_manager_b200.build" in out.stdout
+
+
+def test_the_dockerfile_build_stage_command_really_builds_the_library(tmp_path):
+    """No docker here — but stage 2 of the image is one RUN line on top of the same CUDA toolkit this
+    container has: execute exactly that line on a copy of what the stage COPYs, and check the artefacts."""
+    import re
+    import shutil
+    import subprocess as sp
+    stage = DOCKERFILE[DOCKERFILE.index("AS ccm"):DOCKERFILE.index("# Stage 3")]
+    copies = re.findall(r"^COPY (\S+) (\S+)$", stage, re.M)
+    assert copies == [("include/", "include/"), ("k8s_cc_manager_b200/", "k8s_cc_manager_b200/")]
+    for src, dst in copies:
+        shutil.copytree(ROOT / src, tmp_path / dst,
+                        ignore=shutil.ignore_patterns("*.so", "ccm-scrub", "__pycache__"))
+    run = stage[stage.index("RUN ") + 4:].replace("\\\n", " ").strip()
+    proc = sp.run(["bash", "-c", run], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    lib, cli = tmp_path / "k8s_cc_manager_b200" / "libccm.so", tmp_path / "k8s_cc_manager_b200" / "ccm-scrub"
+    assert lib.exists() and cli.exists()
+    nm = sp.run(["nm", "-D", "--defined-only", str(lib)], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (ccm_[a-z0-9_]+)", nm))
+    header = (ROOT / "include" / "ccm.h").read_text()
+    declared = set(re.findall(r"^\s*(?:const char\*|int|uint64_t)\s+(ccm_[a-z0-9_]+)\s*\(", header, re.M))
+    assert exported == declared
+    sass = sp.run(["cuobjdump", "-lelf", str(lib)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass and "sm_90" not in sass, "the image must carry sm_100a code only"
+    # the CLI finds the library next to itself ($ORIGIN rpath) and fails closed without a GPU
+    out = sp.run([str(cli), "--all", "--backend", "sim"], capture_output=True, text=True,
+                 env={"CCM_SIM_GPUS": "2", "CCM_SIM_BIND_CUDA": "0", "PATH": "/usr/bin:/bin"}, timeout=60)
+    assert out.returncode == 3 and '"status": -9' in out.stdout
