@@ -210,12 +210,27 @@ def recover_journaled_labels(v1, node_name: str) -> Optional[Dict[str, str]]:
     return {k: str(v) for k, v in data.items() if k in COMPONENT_APP_LABELS}
 
 
-def set_cc_state_label(v1, node_name: str, state: str) -> bool:
+def set_cc_state_label(v1, node_name: str, state: str, *,
+                       regate: Optional[Callable[[], bool]] = None) -> bool:
     """Publish the outcome: cc.mode.state=<state>, cc.ready.state = true for on/ppcie,
-    false for off, empty for anything else (devtools, failed)."""
-    ready = _READY_FOR_STATE.get(state, "")
+    false for off, empty for anything else (devtools, failed).
+
+    regate (optional, not in the reference): called when the node read that precedes the patch shows
+    cc.mode.state=failed, i.e. the LAST transition did not pass; it must return True for `state` to be
+    published, otherwise 'failed' stays.  The check rides on the read the reference does anyway
+    (read_node, mutate, patch_node), so the healthy path keeps exactly the reference's two API verbs;
+    only after a (slow) regate is the node read again before it is patched."""
     try:
-        _patch_labels(v1, node_name, {CC_MODE_STATE_LABEL: state, CC_READY_STATE_LABEL: ready})
+        node = v1.read_node(node_name)
+        if regate is not None and (node.metadata.labels or {}).get(CC_MODE_STATE_LABEL) == "failed":
+            if not regate():
+                state = "failed"
+            node = v1.read_node(node_name)          # the gate took a while: patch a fresh copy
+        ready = _READY_FOR_STATE.get(state, "")
+        if node.metadata.labels is None:
+            node.metadata.labels = {}
+        node.metadata.labels.update({CC_MODE_STATE_LABEL: state, CC_READY_STATE_LABEL: ready})
+        v1.patch_node(node_name, node)
         logger.info("Set %s=%s, %s=%s", CC_MODE_STATE_LABEL, state, CC_READY_STATE_LABEL, ready)
         return True
     except ApiException as exc:

@@ -46,7 +46,6 @@ from kubernetes.client.rest import ApiException
 from . import devices as _devices
 from .devices import GpuError
 from .drain_gate import (
-    CC_MODE_STATE_LABEL,
     evict_gpu_operator_components,
     fetch_current_component_labels,
     recover_journaled_labels,
@@ -320,42 +319,39 @@ class CCManager:
             return True
         if self.mode_is_set(cc_gpus, mode):
             logger.info("All gpus already set to cc %s, skipping", mode)
-            if not self._regate_if_last_transition_failed(cc_gpus, mode):
-                return False
-            set_cc_state_label(self.v1, self.node_name, mode)
-            return True
+            return self._publish_already_set(cc_gpus, mode)
         if self.evict_operator_components:
             return self._set_cc_mode_with_eviction(cc_gpus, mode)
         return self._set_cc_mode_direct(cc_gpus, mode)
 
-    def _regate_if_last_transition_failed(self, gpus: list, mode: str) -> bool:
-        """The registers already read `mode`, but the node still carries cc.mode.state=failed: the
-        last transition flipped the GPUs and then did NOT pass (e.g. the HBM scrub found dirt, or the
-        manager died before the verdict).  Publishing `mode` now would turn that failure into a
-        success without a single byte having been checked — so the gate runs first.
-        Only with a gate configured (require/auto); costs one node read on this path."""
+    def _publish_already_set(self, gpus: list, mode: str) -> bool:
+        """reference main.py:255-258: the registers already read `mode`, publish it.  One addition: if the
+        node still carries cc.mode.state=failed, the last transition flipped the GPUs and then did NOT pass
+        (e.g. the HBM scrub found dirt, or the manager died before the verdict).  Publishing `mode` now would
+        turn that failure into a success without a single byte having been checked — so the gate
+        runs first.  The check rides on the node read that set_cc_state_label does anyway: the healthy path
+        costs exactly the reference's two API verbs, with or without a gate configured."""
         if self.scrub_mode == "skip":
+            set_cc_state_label(self.v1, self.node_name, mode)
             return True
-        try:
-            labels = self.v1.read_node(self.node_name).metadata.labels or {}
-        except ApiException as exc:
-            logger.warning("Could not read %s before publishing the state: %s", CC_MODE_STATE_LABEL, exc)
-            return True
-        if labels.get(CC_MODE_STATE_LABEL) != "failed":
-            return True
-        logger.warning("GPUs already read CC mode '%s' but the last transition FAILED: running the HBM scrub gate "
-                       "before the state is published", mode)
-        self.last_transition = {"mode": mode, "gpus": len(gpus), "phase_seconds": {}, "regate": True}
-        t0 = time.perf_counter()
-        try:
-            self._scrub_gate(gpus)
-        except Exception as exc:  # noqa: BLE001 - GpuError, ScrubFailure, anything: stay failed
-            logger.error("HBM scrub gate failed again: %s", exc)
-            self._finish_transition("failed", t0)
-            return False
-        self.last_transition["seconds_to_verdict"] = time.perf_counter() - t0
-        self._release_gate_resources()
-        return True
+        outcome = {"ok": True}
+
+        def regate() -> bool:
+            logger.warning("GPUs already read CC mode '%s' but the last transition FAILED: running the HBM scrub "
+                           "gate before the state is published", mode)
+            self.last_transition = {"mode": mode, "gpus": len(gpus), "phase_seconds": {}, "regate": True}
+            t0 = time.perf_counter()
+            try:
+                self._scrub_gate(gpus)
+            except Exception as exc:  # noqa: BLE001 - GpuError, ScrubFailure, anything: stay failed
+                logger.error("HBM scrub gate failed again: %s", exc)
+                outcome["ok"] = False
+            self.last_transition["seconds_to_verdict"] = time.perf_counter() - t0
+            return outcome["ok"]
+
+        set_cc_state_label(self.v1, self.node_name, mode, regate=regate)
+        self._release_gate_resources()      # no-op unless the gate ran; after the label, as everywhere
+        return outcome["ok"]
 
     def set_ppcie_mode(self) -> bool:
         """Protected-PCIe mode on every GPU and NVSwitch (reference main.py:265-296)."""

@@ -152,9 +152,11 @@ def test_a_failed_gate_is_not_laundered_by_a_restart(monkeypatch):
     dev._report = None
     dev.ops.clear()
     assert mgr2.set_cc_mode("on") is True and state(c) == "on" and dev.ops == ["scrub"]
-    # and a healthy already-set node costs no scrub at all
+    # and a healthy already-set node costs no scrub at all — and exactly the reference's two API verbs
     dev.ops.clear()
+    c.calls.clear()
     assert mgr2.set_cc_mode("on") is True and dev.ops == []
+    assert c.verbs() == ["read_node", "patch_node"]
 
 
 def test_skip_mode_keeps_the_reference_early_out_verbatim(monkeypatch):
