@@ -769,16 +769,18 @@ def constructed_baselines(L, N, n_gpus, args):
         assert mgr.set_cc_mode("on") is True
         ts.append(time.perf_counter() - t0)
     ref = None
-    try:
-        ref = json.loads((ROOT / "profiles" / "r1_config1_get_only.json").read_text())
-    except Exception:  # noqa: BLE001
-        pass
+    for name in ("r2_config1_get_only.json", "r1_config1_get_only.json"):
+        try:
+            ref = json.loads((ROOT / "profiles" / name).read_text())
+            break
+        except Exception:  # noqa: BLE001
+            pass
     out["B0_get_only"] = {"product_us_median": statistics.median(ts) * 1e6, "gpus": n_gpus,
                           "what": "configs[0]: set_cc_mode(mode) with every GPU already in `mode` (reference main.py:232-258): "
                                   "N register reads + state label; sim registers, in-memory API",
-                          "reference_main_py_committed": ref and {k: ref[k] for k in ref if "us" in k or "note" in k or "what" in k},
+                          "reference_main_py_committed": ref and {k: (v if not isinstance(v, dict) else v.get("median_us")) for k, v in ref.items()},
                           "reference_note": "the unmodified reference cannot run on the GPU box (/root/reference is not there); "
-                                            "its number was taken in the dev container: profiles/r1_config1_get_only.json"}
+                                            "its numbers (median us per call) were taken in the dev container by benchmarks/config1_get_only.py: profiles/r2_config1_get_only.json"}
     L.ccm_sim_set(-1, b"cc_mode", 0)
     return out
 
