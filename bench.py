@@ -753,7 +753,13 @@ def constructed_baselines(L, N, n_gpus, args):
                  "sample_bytes_per_gpu": sample,
                  "what": "constructed: GPUs one after another, cudaMemset + host verify over PCIe "
                          "(256 MiB pinned D2H + np.count_nonzero, one thread); bounded sample, throughput extrapolates linearly"}
-    # B0: the get-only plumbing path (BASELINE configs[0]) through the product
+    out["B0_get_only"] = b0_get_only(L, N, n_gpus)
+    return out
+
+
+def b0_get_only(L, N, n_gpus, reps=200):
+    """B0: the get-only plumbing path (BASELINE configs[0]) through the product — set_cc_mode(mode) with every
+    GPU already in `mode` (reference main.py:232-258): N register reads + the state label."""
     from k8s_cc_manager_b200 import devices as D
     from k8s_cc_manager_b200 import manager
     import kubernetes
@@ -764,7 +770,7 @@ def constructed_baselines(L, N, n_gpus, args):
     first_n = lambda: tuple(x[:n_gpus] if isinstance(x, list) else n_gpus for x in D.find_gpus())  # noqa: E731
     mgr = manager.CCManager("bench-node", "on", True, device_source=first_n, scrub_mode="skip")
     ts = []
-    for _ in range(200):
+    for _ in range(reps):
         t0 = time.perf_counter()
         assert mgr.set_cc_mode("on") is True
         ts.append(time.perf_counter() - t0)
@@ -775,14 +781,14 @@ def constructed_baselines(L, N, n_gpus, args):
             break
         except Exception:  # noqa: BLE001
             pass
-    out["B0_get_only"] = {"product_us_median": statistics.median(ts) * 1e6, "gpus": n_gpus,
+    result = {"product_us_median": statistics.median(ts) * 1e6, "gpus": n_gpus,
                           "what": "configs[0]: set_cc_mode(mode) with every GPU already in `mode` (reference main.py:232-258): "
                                   "N register reads + state label; sim registers, in-memory API",
                           "reference_main_py_committed": ref and {k: (v if not isinstance(v, dict) else v.get("median_us")) for k, v in ref.items()},
                           "reference_note": "the unmodified reference cannot run on the GPU box (/root/reference is not there); "
                                             "its numbers (median us per call) were taken in the dev container by benchmarks/config1_get_only.py: profiles/r2_config1_get_only.json"}
     L.ccm_sim_set(-1, b"cc_mode", 0)
-    return out
+    return result
 
 
 # --------------------------------------------------------------------------- sweep

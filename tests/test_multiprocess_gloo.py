@@ -117,3 +117,15 @@ def test_cpu_arm_reports_best_and_median_with_numa_layout():
     assert cb["best"] >= cb["median"] > 0 and cb["value"] > 0
     assert "NUMA" in cb["sample"] and "pinned" in cb["sample"]
     assert {c["scrub"] for c in cb["tuning"]} == {"memset", "nt-stores"}
+
+
+def test_bench_b0_get_only_runs_on_the_sim_backend(native, cluster):
+    """bench.py's node leg, the part that needs no GPU: configs[0] through the product on simulated registers."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    L = native.lib()
+    assert L.ccm_sim_topology(8, 0) == 0
+    out = bench.b0_get_only(L, native, 4, reps=20)
+    assert out["gpus"] == 4 and 1.0 < out["product_us_median"] < 5000.0
+    ref = out["reference_main_py_committed"]
+    assert ref and ref["reference_fake_devices"] > 0 and ref["product_serial"] > 0
