@@ -424,15 +424,44 @@ static int run_multi(int n, const char* mode, size_t cap_gib) {
   return 0;
 }
 
+// ctx: how long do primary-context creation and reset take (warm process), and do environment knobs that
+// shrink a context (CUDA_DEVICE_MAX_CONNECTIONS=1 -> fewer channels) make them cheaper?
+static int run_ctx(int reps) {
+  DR(cuInit(0));
+  CUdevice dev;
+  DR(cuDeviceGet(&dev, 0));
+  const char* mc = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+  printf("CUDA_DEVICE_MAX_CONNECTIONS=%s\n", mc ? mc : "(default 8)");
+  for (int i = 0; i < reps; ++i) {
+    CUcontext ctx;
+    double a = now_ms();
+    DR(cuDevicePrimaryCtxRetain(&ctx, dev));
+    DR(cuCtxSetCurrent(ctx));
+    double b = now_ms();
+    touch<<<148, 256>>>(nullptr, 0);  // first launch: module load
+    DR(cuCtxSynchronize());
+    double c = now_ms();
+    size_t fr = 0, tot = 0;
+    DR(cuMemGetInfo(&fr, &tot));
+    DR(cuDevicePrimaryCtxRelease(dev));
+    DR(cuDevicePrimaryCtxReset(dev));
+    double d = now_ms();
+    printf("ctx rep %d: create %.1f ms, first launch %.1f ms, release+reset %.1f ms, context footprint %.0f MiB\n", i, b - a, c - b,
+           d - c, (tot - fr) / 1048576.0);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   g_t0 = now_ms();
   setvbuf(stdout, nullptr, _IOLBF, 0);
+  if (argc >= 2 && !strcmp(argv[1], "ctx")) return run_ctx(argc >= 3 ? atoi(argv[2]) : 5);
   if (argc >= 2 && !strcmp(argv[1], "single")) return run_single(argc >= 3 ? strtoull(argv[2], nullptr, 10) : 0);
   if (argc >= 3 && !strcmp(argv[1], "multi")) {
     const char* g0 = getenv("VMM_PROBE_T0");
     if (g0) g_t0 = atof(g0);
     return run_multi(atoi(argv[2]), argc >= 4 ? argv[3] : "procs", argc >= 5 ? strtoull(argv[4], nullptr, 10) : 0);
   }
-  printf("usage: vmm_probe single [gib] | multi N [procs|threads|procs-stagger] [gib]\n");
+  printf("usage: vmm_probe single [gib] | multi N [procs|threads|procs-stagger] [gib] | ctx [reps]\n");
   return 2;
 }

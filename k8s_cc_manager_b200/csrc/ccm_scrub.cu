@@ -41,7 +41,25 @@ static double now_ms() {
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// A CUDA context is as expensive as the number of hardware work queues ("connections") it sets up, and
+// the scrub engine drives exactly ONE stream per GPU.  Measured on B200 (benchmarks/vmm_probe.cu ctx,
+// profiles/r2_ctx_connections.log): primary-context creation 138 ms -> 70 ms and reset 170 ms -> 76 ms with
+// CUDA_DEVICE_MAX_CONNECTIONS=1 instead of the default 8 (32: 0.7-1 s and 0.8-3 s).  Context creation and
+// teardown are what a transition on 8 GPUs mostly consists of, and the driver serialises
+// them across GPUs — so the library asks for one connection unless the host process chose a value itself
+// (the variable is only read when CUDA initialises; CCM_CUDA_MAX_CONNECTIONS=0 leaves CUDA's default,
+// any other number is passed through).
+static void apply_cuda_env_defaults() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* want = getenv("CCM_CUDA_MAX_CONNECTIONS");
+    if (want && !strcmp(want, "0")) return;
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", want && *want ? want : "1", 0 /* never override the host's own choice */);
+  });
+}
+
 int cuda_device_count() {
+  apply_cuda_env_defaults();
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -168,6 +186,7 @@ static std::vector<std::unique_ptr<ScrubEngine>> g_engines;
 
 ScrubEngine* engine_for(int ordinal) {
   if (ordinal < 0) { set_error("device has no CUDA ordinal"); return nullptr; }
+  apply_cuda_env_defaults();
   ScrubEngine* e = nullptr;
   {
     std::lock_guard<std::mutex> g(g_engines_mu);

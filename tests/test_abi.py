@@ -4,6 +4,7 @@ layouts seen through ctypes match the header; the scrub fails LOUDLY without CUD
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 import subprocess
 from pathlib import Path
@@ -116,3 +117,18 @@ def test_traffic_json_is_keyed_by_the_kernels_auto_launches(native):
         assert 0.98 * tr["region_bytes"] < k["dram_bytes_read"] + k["dram_bytes_write"] < 1.02 * tr["region_bytes"]
     src = (ROOT / "k8s_cc_manager_b200" / "csrc" / "ccm_scrub.cu").read_text()
     assert "launch_fast(CCM_FAST_SCRUB" in src and "launch_fast(CCM_FAST_VERIFY" in src
+
+
+def test_library_asks_for_one_cuda_connection_unless_the_host_chose(native):
+    """libccm drives ONE stream per GPU; a context with 1 hardware queue is created and reset in half the time
+    of the default 8 (profiles/r2_ctx_connections.log).  The host's own choice is never overridden."""
+    import subprocess, sys
+    code = ("import ctypes as C, os, sys; sys.path.insert(0, %r); from k8s_cc_manager_b200 import _native as N; "
+            "n = C.c_int(); N.lib().ccm_enumerate(None, 0, C.byref(n)); "
+            "g = C.CDLL(None).getenv; g.restype = C.c_char_p; print(g(b'CUDA_DEVICE_MAX_CONNECTIONS'))" % str(ROOT))
+    base = {k: v for k, v in os.environ.items() if k not in ("CUDA_DEVICE_MAX_CONNECTIONS", "CCM_CUDA_MAX_CONNECTIONS")}
+    run = lambda env: subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, check=True).stdout.strip()  # noqa: E731
+    assert run(base) == "b'1'"
+    assert run(dict(base, CUDA_DEVICE_MAX_CONNECTIONS="4")) == "b'4'"            # the host's choice stands
+    assert run(dict(base, CCM_CUDA_MAX_CONNECTIONS="0")) == "None"               # opt out: CUDA's default
+    assert run(dict(base, CCM_CUDA_MAX_CONNECTIONS="2")) == "b'2'"
